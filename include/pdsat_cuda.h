@@ -1,0 +1,188 @@
+/* pdsat_cuda.h — C-ABI boundary of the B200-native PDSAT hot path.
+ *
+ * The reference (Nauchnik/pdsat) has no plugin / FFI interface; the seam is cut where
+ * SURVEY.md §8(b) puts it.  Each entry point names the reference code it replaces
+ * (paths relative to the reference root).  The library is libpdsat_b200.so, built from
+ * pdsat_b200/csrc/ for sm_100a; there is NO CPU fallback behind these calls: without a
+ * CUDA device every compute entry point fails with PDSAT_ERR_CUDA.
+ *
+ * Data contract:
+ *   - literals are MiniSat `Lit.x` = 2*var + sign, var 0-based, sign 1 = negated
+ *     (src_common/minisat/core/SolverTypes.h:46-62);
+ *   - decomposition-set variables are 1-based DIMACS indices, as in
+ *     decomp_set::var_choose_order (src_mpi/mpi_predicter.h:58-64);
+ *   - lbool bytes: 0 true, 1 false, 2 undefined (SolverTypes.h:84-115).
+ *
+ * Threading: one pdsat_db per GPU; calls on one handle (and its batches) are serialised
+ * by the caller (the reference is one single-threaded process per MPI rank).
+ * Errors: int status, message via pdsat_last_error(); the library never exits.
+ */
+#ifndef PDSAT_CUDA_H
+#define PDSAT_CUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pdsat_db pdsat_db;       /* clause database resident in one GPU's HBM */
+typedef struct pdsat_batch pdsat_batch; /* device buffers of one batch of samples      */
+
+enum {
+    PDSAT_OK = 0,
+    PDSAT_ERR_ARG = 1,   /* bad argument                                              */
+    PDSAT_ERR_CUDA = 2,  /* CUDA runtime error / no device                            */
+    PDSAT_ERR_UNSAT = 3, /* instance refuted at level 0 (Solver::ok == false)         */
+    PDSAT_ERR_LIMIT = 4  /* instance exceeds a structural limit of the kernels        */
+};
+
+/* How the values of the decomposition-set variables of sample s are obtained. */
+enum {
+    /* bit j of sample s = bool_rand of draw (first_sample+s)*k + j of mt19937(seed):
+     * the reference's 1-worker order (src_mpi/mpi_predicter.cpp:3236-3242,
+     * src_common/addit_func.cpp:193-196; bool_rand == ((draw >> 31) == 0)). */
+    PDSAT_MODE_RANDOM_MT19937 = 0,
+    /* declared counter-based generator (NOT the reference stream): the 64 values of set
+     * position j for samples [64g, 64g+64) are the bits of
+     * splitmix64(seed + 0x9E3779B97F4A7C15 * (g * 65536 + j + 1)), g counted from
+     * first_sample / 64 (first_sample must be a multiple of 64). */
+    PDSAT_MODE_RANDOM_COUNTER = 1,
+    /* solve-mode enumeration: sample s is assignment index lint = first_sample + s;
+     * bit r of lint is the value of set_vars[r]
+     * (src_mpi/mpi_base.cpp:148-169 MakeAssignsFromMasks; pass set_vars ascending). */
+    PDSAT_MODE_ENUM = 2,
+    /* values supplied by the caller: explicit_values[s*k + j] in {0,1}
+     * (te > 0 mode: known states + keystream, src_mpi/mpi_predicter.cpp:3188-3235). */
+    PDSAT_MODE_EXPLICIT = 3
+};
+
+/* One point = one decomposition set and its sample range.  A true value makes the
+ * POSITIVE literal of the variable the assumption (mpi_predicter.cpp:3241). */
+typedef struct {
+    const int32_t* set_vars;         /* k variables, 1-based                           */
+    int32_t k;
+    int32_t mode;                    /* PDSAT_MODE_*                                   */
+    uint64_t seed;                   /* RANDOM modes (reference: the worker's rank)    */
+    uint64_t first_sample;
+    uint64_t n_samples;
+    const uint8_t* explicit_values;  /* EXPLICIT mode only: n_samples * k bytes        */
+} pdsat_point;
+
+/* Integer-exact Monte Carlo accumulators of one point: what GetPredict needs
+ * (src_mpi/mpi_predicter.cpp:1904-2115).  `trail` of a sample is the
+ * number of assigned variables at the BCP fixpoint (level-0 units + fixed assumptions +
+ * set variables + implied) = Solver::propagations of a conflict-free sample. */
+#define PDSAT_COST_WORDS 8
+typedef struct {
+    uint64_t n;            /* samples evaluated                                        */
+    uint64_t n_conflict;   /* BCP conflict  (ret == l_False, isSolvedOnPreprocessing)  */
+    uint64_t n_full;       /* BCP assigned every variable: a model (ret == l_True)     */
+    uint64_t sum_trail;    /* over conflict-free samples                               */
+    uint64_t sumsq_trail;  /* over conflict-free samples                               */
+    uint64_t n_implied_any;/* conflict-free samples where BCP implied >= 1 literal     */
+    uint64_t reserved[2];
+} pdsat_cost;
+
+typedef struct {
+    int32_t n_vars;          /* as uploaded                                            */
+    int32_t n_live_vars;     /* not assigned by level-0 units / fixed assumptions      */
+    int64_t n_clauses_in;    /* as uploaded                                            */
+    int64_t n_clauses_live;  /* after addClause_ normalisation + level-0 simplification*/
+    int64_t n_lits_live;
+    int32_t n_base_assigned; /* level-0 trail size incl. fixed assumptions             */
+    int32_t max_clause_len;
+    int32_t status;          /* PDSAT_OK or PDSAT_ERR_UNSAT                            */
+    int32_t warps_per_cta;   /* launch shape chosen for the BCP kernel                 */
+    int32_t smem_bytes;      /* dynamic shared memory per CTA                          */
+    int32_t grid;            /* CTAs launched                                          */
+    int32_t db_in_smem;      /* 1 = clause records staged in shared memory            */
+    int32_t sm_count;
+} pdsat_db_info;
+
+/* output selection for pdsat_batch_create */
+enum {
+    PDSAT_OUT_FLAGS = 1,  /* per-sample conflict / full bitmaps                        */
+    PDSAT_OUT_TRAIL = 2,  /* per-sample trail size (uint16)                            */
+    PDSAT_OUT_ASSIGN = 4  /* per-sample assignment of every variable (parity tests)    */
+};
+
+const char* pdsat_last_error(void);
+int pdsat_device_count(int* n);
+
+/* ---- clause database upload ----------------------------------------------------------
+ * Replaces Solver::addProblem + addClause_ + attachClause
+ * (src_common/minisat/core/Solver.h:478-492, Solver.cc:279-317) executed once per sample
+ * by solverProgramCalling (src_mpi/mpi_predicter.cpp:703-705).  Input is the `Problem`
+ * produced by minisat22_wrapper::parse_DIMACS_to_problem (src_common/minisat22_wrapper.cpp:43-69)
+ * flattened to CSR.  Applies the addClause_ rules (sort, duplicate / tautology removal),
+ * folds level-0 units by one host BCP and builds the flat clause-record + occurrence-list
+ * layout in HBM.  A level-0 conflict is reported through pdsat_db_get_info().status and by
+ * every later evaluate call counting all samples as conflicts (Solver::ok == false).
+ * Host buffers stay owned by the caller. */
+int pdsat_upload_cnf(int device, int32_t n_vars, int64_t n_clauses, const uint32_t* offsets,
+                     const int32_t* lits, pdsat_db** out);
+
+/* Literals assumed in EVERY sample: the keystream bits of a cipher instance
+ * (src_mpi/mpi_predicter.cpp:3229-3234) or solve mode's known_dummy
+ * (src_mpi/mpi_solver.cpp:199-200).  They are folded into the level-0 assignment by host
+ * BCP and the device database is rebuilt; n = 0 restores the plain template. */
+int pdsat_set_fixed_assumptions(pdsat_db* db, const int32_t* lits, int32_t n);
+
+int pdsat_db_get_info(const pdsat_db* db, pdsat_db_info* info);
+/* level-0 assignment incl. fixed assumptions, n_vars lbool bytes */
+int pdsat_db_base_assignment(const pdsat_db* db, uint8_t* assigns);
+/* run on a caller-owned cudaStream_t (e.g. torch's current stream); NULL = own stream */
+int pdsat_set_stream(pdsat_db* db, void* cuda_stream);
+void pdsat_destroy(pdsat_db* db);
+
+/* ---- batch evaluate --------------------------------------------------------------------
+ * Replaces, for a whole batch, solvePredictSatInstance + solverProgramCalling
+ * (src_mpi/mpi_predicter.cpp:3183-3277, 691-773) with evaluation_type "prep" /
+ * "propagation", and SolverRun's BCP-decided share (src_mpi/mpi_solver.cpp:167-294).
+ * Several points (a tabu neighbourhood, mpi_predicter.cpp:2926-2935) go in one batch. */
+int pdsat_batch_create(pdsat_db* db, int32_t n_points, const pdsat_point* points, uint32_t out_flags,
+                       int32_t max_models, pdsat_batch** out);
+/* change the stream position of a point without reallocating (RANDOM / ENUM modes) */
+int pdsat_batch_reseed(pdsat_batch* b, int32_t point, uint64_t seed, uint64_t first_sample);
+/* stage 1 (async): sample values -> bit-sliced assumption words in HBM */
+int pdsat_batch_fill(pdsat_batch* b);
+/* stage 2 (async): BCP of every sample + per-point cost accumulation */
+int pdsat_batch_propagate(pdsat_batch* b);
+int pdsat_batch_sync(pdsat_batch* b);
+/* device time of the last fill / propagate on this batch, CUDA events on the launch stream */
+int pdsat_batch_last_ms(pdsat_batch* b, float* fill_ms, float* propagate_ms);
+int pdsat_batch_launch_count(pdsat_batch* b, int64_t* n_kernels);
+
+/* ---- cost reduce -------------------------------------------------------------------------
+ * Replaces the per-sample MPI replies (mpi_predicter.cpp:3266-3270) and their storage
+ * (:504-516).  The accumulators live in HBM as n_points * PDSAT_COST_WORDS uint64; the
+ * device pointer is exposed so that ranks can ncclAllReduce(sum, uint64) it in place. */
+int pdsat_batch_cost_device_ptr(pdsat_batch* b, void** dptr);
+/* use a caller-owned device buffer (n_points * PDSAT_COST_WORDS uint64) instead */
+int pdsat_batch_set_cost_buffer(pdsat_batch* b, void* dptr);
+int pdsat_batch_costs(pdsat_batch* b, pdsat_cost* out /* n_points */);
+
+/* ---- per-sample results (optional outputs) ------------------------------------------- */
+/* bit s%64 of word s/64 (s counted inside the point) */
+int pdsat_batch_flags(pdsat_batch* b, int32_t point, uint64_t* conflict_bits, uint64_t* full_bits);
+int pdsat_batch_trail(pdsat_batch* b, int32_t point, uint16_t* trail /* n_samples */);
+/* lbool bytes [n][n_vars] for samples first..first+n-1 of the point */
+int pdsat_batch_assign(pdsat_batch* b, int32_t point, uint64_t first, uint64_t n, uint8_t* assigns);
+/* models found by BCP alone (b_SAT_set_array, mpi_predicter.cpp:760-762): *n_found is the
+ * total, at most max_models are stored; models[i*n_vars + v] in {0,1} (1 = true) */
+int pdsat_batch_models(pdsat_batch* b, int64_t* n_found, int32_t* point_of, uint64_t* sample_of,
+                       uint8_t* models);
+void pdsat_batch_destroy(pdsat_batch* b);
+
+/* ---- one-call form (host buffers in, host buffers out; the e2e path) ---------------- */
+int pdsat_eval_batch(pdsat_db* db, int32_t n_points, const pdsat_point* points, pdsat_cost* costs);
+
+/* mt19937 bool_rand bits produced by the device generator, for stream-parity tests:
+ * out[i] = bool_rand of draw first+i */
+int pdsat_mt19937_bool_rand(int device, uint32_t seed, uint64_t first, uint64_t n, uint8_t* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PDSAT_CUDA_H */

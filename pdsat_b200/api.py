@@ -1,0 +1,315 @@
+"""ctypes binding of libpdsat_b200.so (the C-ABI in include/pdsat_cuda.h).
+
+This is plumbing for tests and bench.py; the product is the CUDA library.  There is no
+CPU fallback: if the shared library is missing, or no CUDA device is present, the calls
+raise.  Nothing in this package imports the CPU oracle.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libpdsat_b200.so")
+
+PDSAT_OK, PDSAT_ERR_ARG, PDSAT_ERR_CUDA, PDSAT_ERR_UNSAT, PDSAT_ERR_LIMIT = 0, 1, 2, 3, 4
+MODE_MT19937, MODE_COUNTER, MODE_ENUM, MODE_EXPLICIT = 0, 1, 2, 3
+OUT_FLAGS, OUT_TRAIL, OUT_ASSIGN = 1, 2, 4
+COST_WORDS = 8
+
+EXPORTS = [
+    "pdsat_last_error", "pdsat_device_count", "pdsat_upload_cnf", "pdsat_set_fixed_assumptions",
+    "pdsat_db_get_info", "pdsat_db_base_assignment", "pdsat_set_stream", "pdsat_destroy",
+    "pdsat_batch_create", "pdsat_batch_reseed", "pdsat_batch_fill", "pdsat_batch_propagate",
+    "pdsat_batch_sync", "pdsat_batch_last_ms", "pdsat_batch_launch_count", "pdsat_batch_cost_device_ptr",
+    "pdsat_batch_set_cost_buffer", "pdsat_batch_costs", "pdsat_batch_flags", "pdsat_batch_trail",
+    "pdsat_batch_assign", "pdsat_batch_models", "pdsat_batch_destroy", "pdsat_eval_batch",
+    "pdsat_mt19937_bool_rand",
+]
+
+
+class PdsatError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__("pdsat error %d: %s" % (code, msg))
+        self.code = code
+
+
+class CPoint(C.Structure):
+    _fields_ = [("set_vars", C.c_void_p), ("k", C.c_int32), ("mode", C.c_int32), ("seed", C.c_uint64),
+                ("first_sample", C.c_uint64), ("n_samples", C.c_uint64), ("explicit_values", C.c_void_p)]
+
+
+class CCost(C.Structure):
+    _fields_ = [("n", C.c_uint64), ("n_conflict", C.c_uint64), ("n_full", C.c_uint64), ("sum_trail", C.c_uint64),
+                ("sumsq_trail", C.c_uint64), ("n_implied_any", C.c_uint64), ("reserved", C.c_uint64 * 2)]
+
+
+class CDbInfo(C.Structure):
+    _fields_ = [("n_vars", C.c_int32), ("n_live_vars", C.c_int32), ("n_clauses_in", C.c_int64),
+                ("n_clauses_live", C.c_int64), ("n_lits_live", C.c_int64), ("n_base_assigned", C.c_int32),
+                ("max_clause_len", C.c_int32), ("status", C.c_int32), ("warps_per_cta", C.c_int32),
+                ("smem_bytes", C.c_int32), ("grid", C.c_int32), ("db_in_smem", C.c_int32), ("sm_count", C.c_int32)]
+
+
+_lib = None
+
+
+def lib():
+    """Load the CUDA library; fail loudly if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError("%s is missing: build it with `python -m pdsat_b200.build` "
+                           "(the CUDA path has no CPU fallback)" % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    L.pdsat_last_error.restype = C.c_char_p
+    L.pdsat_device_count.argtypes = [C.POINTER(C.c_int)]
+    L.pdsat_upload_cnf.argtypes = [C.c_int, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
+    L.pdsat_set_fixed_assumptions.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
+    L.pdsat_db_get_info.argtypes = [C.c_void_p, C.POINTER(CDbInfo)]
+    L.pdsat_db_base_assignment.argtypes = [C.c_void_p, C.c_void_p]
+    L.pdsat_set_stream.argtypes = [C.c_void_p, C.c_void_p]
+    L.pdsat_destroy.argtypes = [C.c_void_p]
+    L.pdsat_destroy.restype = None
+    L.pdsat_batch_create.argtypes = [C.c_void_p, C.c_int32, C.POINTER(CPoint), C.c_uint32, C.c_int32,
+                                     C.POINTER(C.c_void_p)]
+    L.pdsat_batch_reseed.argtypes = [C.c_void_p, C.c_int32, C.c_uint64, C.c_uint64]
+    L.pdsat_batch_fill.argtypes = [C.c_void_p]
+    L.pdsat_batch_propagate.argtypes = [C.c_void_p]
+    L.pdsat_batch_sync.argtypes = [C.c_void_p]
+    L.pdsat_batch_last_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    L.pdsat_batch_launch_count.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
+    L.pdsat_batch_cost_device_ptr.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+    L.pdsat_batch_set_cost_buffer.argtypes = [C.c_void_p, C.c_void_p]
+    L.pdsat_batch_costs.argtypes = [C.c_void_p, C.POINTER(CCost)]
+    L.pdsat_batch_flags.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
+    L.pdsat_batch_trail.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
+    L.pdsat_batch_assign.argtypes = [C.c_void_p, C.c_int32, C.c_uint64, C.c_uint64, C.c_void_p]
+    L.pdsat_batch_models.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.c_void_p, C.c_void_p, C.c_void_p]
+    L.pdsat_batch_destroy.argtypes = [C.c_void_p]
+    L.pdsat_batch_destroy.restype = None
+    L.pdsat_eval_batch.argtypes = [C.c_void_p, C.c_int32, C.POINTER(CPoint), C.POINTER(CCost)]
+    L.pdsat_mt19937_bool_rand.argtypes = [C.c_int, C.c_uint32, C.c_uint64, C.c_uint64, C.c_void_p]
+    _lib = L
+    return L
+
+
+def _check(rc: int) -> None:
+    if rc != PDSAT_OK:
+        raise PdsatError(rc, lib().pdsat_last_error().decode())
+
+
+def device_count() -> int:
+    n = C.c_int(0)
+    rc = lib().pdsat_device_count(C.byref(n))
+    return n.value if rc == PDSAT_OK else 0
+
+
+@dataclass
+class Point:
+    """One decomposition set + its sample range (pdsat_point)."""
+    set_vars: Sequence[int]
+    n_samples: int
+    mode: int = MODE_MT19937
+    seed: int = 1
+    first_sample: int = 0
+    explicit_values: Optional[np.ndarray] = None  # [n_samples, k] of {0,1}
+
+
+@dataclass
+class Cost:
+    n: int
+    n_conflict: int
+    n_full: int
+    sum_trail: int
+    sumsq_trail: int
+    n_implied_any: int
+
+
+def _cpoints(points: Sequence[Point]):
+    arr = (CPoint * len(points))()
+    keep = []
+    for i, p in enumerate(points):
+        sv = np.ascontiguousarray(p.set_vars, dtype=np.int32)
+        keep.append(sv)
+        arr[i].set_vars = sv.ctypes.data
+        arr[i].k = len(sv)
+        arr[i].mode = p.mode
+        arr[i].seed = p.seed
+        arr[i].first_sample = p.first_sample
+        arr[i].n_samples = p.n_samples
+        if p.explicit_values is not None:
+            ev = np.ascontiguousarray(p.explicit_values, dtype=np.uint8)
+            assert ev.size == p.n_samples * len(sv)
+            keep.append(ev)
+            arr[i].explicit_values = ev.ctypes.data
+        else:
+            arr[i].explicit_values = None
+    return arr, keep
+
+
+def _costs(arr, n) -> List[Cost]:
+    return [Cost(arr[i].n, arr[i].n_conflict, arr[i].n_full, arr[i].sum_trail, arr[i].sumsq_trail,
+                 arr[i].n_implied_any) for i in range(n)]
+
+
+class ClauseDb:
+    """Clause database on one GPU (pdsat_db).  device=-1 gives a host-only handle used by
+    the CPU tests of the upload logic; it cannot evaluate anything."""
+
+    def __init__(self, n_vars: int, offsets: np.ndarray, lits: np.ndarray, device: int = 0):
+        self.n_vars = int(n_vars)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint32)
+        lits = np.ascontiguousarray(lits, dtype=np.int32)
+        h = C.c_void_p()
+        _check(lib().pdsat_upload_cnf(device, self.n_vars, len(offsets) - 1, offsets.ctypes.data, lits.ctypes.data,
+                                      C.byref(h)))
+        self.h = h
+
+    @classmethod
+    def from_clauses(cls, n_vars: int, clauses, device: int = 0) -> "ClauseDb":
+        from .fixtures import to_csr
+        offs, lits = to_csr(clauses)
+        return cls(n_vars, offs, lits, device)
+
+    def set_fixed_assumptions(self, lits: Sequence[int]) -> None:
+        a = np.ascontiguousarray(lits, dtype=np.int32)
+        _check(lib().pdsat_set_fixed_assumptions(self.h, a.ctypes.data if len(a) else None, len(a)))
+
+    def info(self) -> CDbInfo:
+        i = CDbInfo()
+        _check(lib().pdsat_db_get_info(self.h, C.byref(i)))
+        return i
+
+    def base_assignment(self) -> np.ndarray:
+        a = np.empty(self.n_vars, dtype=np.uint8)
+        _check(lib().pdsat_db_base_assignment(self.h, a.ctypes.data))
+        return a
+
+    def set_stream(self, stream_ptr: int) -> None:
+        _check(lib().pdsat_set_stream(self.h, C.c_void_p(stream_ptr)))
+
+    def eval_batch(self, points: Sequence[Point]) -> List[Cost]:
+        """One call, host buffers in / out (pdsat_eval_batch): the e2e path."""
+        arr, keep = _cpoints(points)
+        out = (CCost * len(points))()
+        _check(lib().pdsat_eval_batch(self.h, len(points), arr, out))
+        return _costs(out, len(points))
+
+    def close(self) -> None:
+        if getattr(self, "h", None):
+            lib().pdsat_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Batch:
+    def __init__(self, db: ClauseDb, points: Sequence[Point], out_flags: int = 0, max_models: int = 0):
+        self.db = db
+        self.points = list(points)
+        arr, keep = _cpoints(self.points)
+        h = C.c_void_p()
+        _check(lib().pdsat_batch_create(db.h, len(self.points), arr, out_flags, max_models, C.byref(h)))
+        self.h = h
+        self.max_models = max_models
+
+    def reseed(self, point: int, seed: int, first_sample: int) -> None:
+        _check(lib().pdsat_batch_reseed(self.h, point, seed, first_sample))
+
+    def fill(self) -> None:
+        _check(lib().pdsat_batch_fill(self.h))
+
+    def propagate(self) -> None:
+        _check(lib().pdsat_batch_propagate(self.h))
+
+    def sync(self) -> None:
+        _check(lib().pdsat_batch_sync(self.h))
+
+    def run(self) -> List[Cost]:
+        self.fill()
+        self.propagate()
+        return self.costs()
+
+    def last_ms(self):
+        f, p = C.c_float(0), C.c_float(0)
+        _check(lib().pdsat_batch_last_ms(self.h, C.byref(f), C.byref(p)))
+        return f.value, p.value
+
+    def launch_count(self) -> int:
+        n = C.c_int64(0)
+        _check(lib().pdsat_batch_launch_count(self.h, C.byref(n)))
+        return n.value
+
+    def cost_device_ptr(self) -> int:
+        p = C.c_void_p()
+        _check(lib().pdsat_batch_cost_device_ptr(self.h, C.byref(p)))
+        return p.value
+
+    def set_cost_buffer(self, dptr: int) -> None:
+        _check(lib().pdsat_batch_set_cost_buffer(self.h, C.c_void_p(dptr)))
+
+    def costs(self) -> List[Cost]:
+        out = (CCost * len(self.points))()
+        _check(lib().pdsat_batch_costs(self.h, out))
+        return _costs(out, len(self.points))
+
+    def flags(self, point: int = 0):
+        """(conflict, full) boolean arrays of the point's samples."""
+        n = self.points[point].n_samples
+        g = (n + 63) // 64
+        c = np.empty(g, dtype=np.uint64)
+        f = np.empty(g, dtype=np.uint64)
+        _check(lib().pdsat_batch_flags(self.h, point, c.ctypes.data, f.ctypes.data))
+        cb = np.unpackbits(c.view(np.uint8), bitorder="little")[:n].astype(bool)
+        fb = np.unpackbits(f.view(np.uint8), bitorder="little")[:n].astype(bool)
+        return cb, fb
+
+    def trail(self, point: int = 0) -> np.ndarray:
+        t = np.empty(self.points[point].n_samples, dtype=np.uint16)
+        _check(lib().pdsat_batch_trail(self.h, point, t.ctypes.data))
+        return t
+
+    def assign(self, point: int = 0, first: int = 0, n: Optional[int] = None) -> np.ndarray:
+        if n is None:
+            n = self.points[point].n_samples - first
+        a = np.empty((n, self.db.n_vars), dtype=np.uint8)
+        _check(lib().pdsat_batch_assign(self.h, point, first, n, a.ctypes.data))
+        return a
+
+    def models(self):
+        """(n_found, point_of, sample_of, models[stored, n_vars])"""
+        cap = max(self.max_models, 1)
+        pts = np.zeros(cap, dtype=np.int32)
+        smp = np.zeros(cap, dtype=np.uint64)
+        mod = np.zeros((cap, self.db.n_vars), dtype=np.uint8)
+        n = C.c_int64(0)
+        _check(lib().pdsat_batch_models(self.h, C.byref(n), pts.ctypes.data, smp.ctypes.data, mod.ctypes.data))
+        stored = min(n.value, self.max_models)
+        return n.value, pts[:stored], smp[:stored], mod[:stored]
+
+    def close(self) -> None:
+        if getattr(self, "h", None):
+            lib().pdsat_batch_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def mt19937_bool_rand(seed: int, first: int, n: int, device: int = 0) -> np.ndarray:
+    out = np.empty(n, dtype=np.uint8)
+    _check(lib().pdsat_mt19937_bool_rand(device, seed, first, n, out.ctypes.data))
+    return out

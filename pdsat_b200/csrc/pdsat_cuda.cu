@@ -1,0 +1,754 @@
+// pdsat_cuda.cu — implementation of the C-ABI declared in include/pdsat_cuda.h.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/pdsat_cuda.h"
+#include "host_db.hpp"
+#include "kernels.cuh"
+#include "mt_jump.hpp"
+
+using namespace pdsat;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+#define CU(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess)                                                                \
+            return fail(PDSAT_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+
+struct pdsat_db {
+    HostDb host;
+    int device = -1;  // -1: host-only handle (CPU tests of the upload logic)
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int sm_count = 0;
+    // device copies
+    uint4* d_rec = nullptr;
+    uint32_t* d_occ_off = nullptr;
+    uint32_t* d_occ = nullptr;
+    DbDev dev{};
+    // launch shape
+    int warps_per_cta = 0, warp_bytes = 0, qcap = 0, smem_bytes = 0, grid = 0;
+};
+
+struct HostPoint {
+    std::vector<int32_t> set_vars;
+    std::vector<uint32_t> setcode;
+    int32_t mode = 0;
+    uint64_t seed = 0, first_sample = 0, n_samples = 0;
+    uint64_t n_groups = 0, group_start = 0, word_off = 0, stream_off = 0, stream_skip = 0, stream_words = 0;
+    uint64_t mt_first_round = 0, mt_rounds = 0;
+    uint32_t n_assumed_live = 0;
+};
+
+struct pdsat_batch {
+    pdsat_db* db = nullptr;
+    std::vector<HostPoint> pts;
+    uint32_t out_flags = 0;
+    int32_t max_models = 0;
+    int32_t model_words = 0;
+    uint64_t n_groups = 0, n_words = 0, n_stream_words = 0;
+    // device
+    PointDev* d_points = nullptr;
+    uint32_t* d_setcode = nullptr;
+    uint64_t* d_words = nullptr;
+    uint32_t* d_stream = nullptr;
+    unsigned long long* d_cost = nullptr;
+    unsigned long long* d_cost_ext = nullptr;
+    uint64_t* d_conflict = nullptr;
+    uint64_t* d_full = nullptr;
+    uint16_t* d_trail = nullptr;
+    uint64_t* d_assign = nullptr;
+    unsigned long long* d_model_count = nullptr;
+    uint32_t* d_model_bits = nullptr;
+    uint32_t* d_model_point = nullptr;
+    uint64_t* d_model_sample = nullptr;
+    // mt19937 segments
+    uint32_t* d_mt_states = nullptr;
+    MtSegment* d_mt_segs = nullptr;
+    uint32_t* h_mt_states = nullptr;  // pinned
+    MtSegment* h_mt_segs = nullptr;   // pinned
+    int n_mt_segs = 0;
+    // explicit values, packed on the host (pinned)
+    uint32_t* h_stream = nullptr;
+    bool has_explicit = false;
+    PointDev* h_points = nullptr;  // pinned mirror
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    bool filled = false, propagated = false;
+    int64_t n_kernels = 0;
+};
+
+extern "C" {
+
+const char* pdsat_last_error(void) { return g_err.c_str(); }
+
+int pdsat_device_count(int* n) {
+    int c = 0;
+    cudaError_t e = cudaGetDeviceCount(&c);
+    if (e != cudaSuccess) {
+        *n = 0;
+        return fail(PDSAT_ERR_CUDA, cudaGetErrorString(e));
+    }
+    *n = c;
+    return PDSAT_OK;
+}
+
+static void free_device_db(pdsat_db* db) {
+    if (db->device < 0) return;
+    cudaFree(db->d_rec);
+    cudaFree(db->d_occ_off);
+    cudaFree(db->d_occ);
+    db->d_rec = nullptr;
+    db->d_occ_off = nullptr;
+    db->d_occ = nullptr;
+}
+
+static int count_bits_for(int n) {
+    int b = 1;
+    while ((1 << b) <= n) b++;
+    return b;
+}
+
+// (re)build the device copy + launch shape from db->host
+static int sync_device_db(pdsat_db* db) {
+    HostDb& h = db->host;
+    if (2 * (int64_t)h.n_live + 2 >= 0xFFFE)
+        return fail(PDSAT_ERR_LIMIT, "more than 32766 live variables: 16-bit literal codes exhausted");
+    if (count_bits_for(h.n_live) > MAX_COUNT_BITS) return fail(PDSAT_ERR_LIMIT, "too many live variables for the counters");
+    int n_lit = 2 * h.n_live;
+    int n_planes = n_lit + 2;
+    int qcap = 4;
+    while (qcap < n_lit + 2) qcap <<= 1;
+    int inq_words = (n_lit + 31) / 32;
+    int warp_bytes = n_planes * 8 + qcap * 2 + ((inq_words + 1) & ~1) * 4 + 16;
+    warp_bytes = (warp_bytes + 15) & ~15;
+    db->qcap = qcap;
+    db->warp_bytes = warp_bytes;
+    if (db->device < 0) {
+        db->warps_per_cta = 0;
+        return PDSAT_OK;
+    }
+    CU(cudaSetDevice(db->device));
+    free_device_db(db);
+    const int max_smem = 227 * 1024;
+    int wpc = max_smem / warp_bytes;
+    if (wpc < 1) return fail(PDSAT_ERR_LIMIT, "assignment state of one sample group exceeds shared memory");
+    if (wpc > 32) wpc = 32;
+    db->warps_per_cta = wpc;
+    db->smem_bytes = wpc * warp_bytes;
+    db->grid = db->sm_count;
+    size_t nrec = (size_t)h.n_rec;
+    CU(cudaMalloc(&db->d_rec, (nrec ? nrec : 1) * sizeof(uint4)));
+    CU(cudaMalloc(&db->d_occ_off, h.occ_off.size() * sizeof(uint32_t)));
+    CU(cudaMalloc(&db->d_occ, (h.occ.size() ? h.occ.size() : 1) * sizeof(uint32_t)));
+    if (nrec) CU(cudaMemcpy(db->d_rec, h.rec.data(), nrec * sizeof(uint4), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(db->d_occ_off, h.occ_off.data(), h.occ_off.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    if (!h.occ.empty())
+        CU(cudaMemcpy(db->d_occ, h.occ.data(), h.occ.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    db->dev.rec = db->d_rec;
+    db->dev.occ_off = db->d_occ_off;
+    db->dev.occ = db->d_occ;
+    db->dev.n_live = h.n_live;
+    db->dev.n_lit = n_lit;
+    db->dev.n_base_assigned = h.n_base_assigned;
+    db->dev.unsat = h.base_ok ? 0 : 1;
+    db->dev.count_bits = count_bits_for(h.n_live);
+    CU(cudaFuncSetAttribute(bcp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    return PDSAT_OK;
+}
+
+int pdsat_upload_cnf(int device, int32_t n_vars, int64_t n_clauses, const uint32_t* offsets, const int32_t* lits,
+                     pdsat_db** out) {
+    if (!out || n_vars < 0 || n_clauses < 0 || (n_clauses > 0 && (!offsets || !lits)))
+        return fail(PDSAT_ERR_ARG, "pdsat_upload_cnf: bad argument");
+    *out = nullptr;
+    pdsat_db* db = new pdsat_db();
+    db->device = device;
+    if (device >= 0) {
+        int cnt = 0;
+        cudaError_t e = cudaGetDeviceCount(&cnt);
+        if (e != cudaSuccess || device >= cnt) {
+            delete db;
+            return fail(PDSAT_ERR_CUDA, e != cudaSuccess ? std::string("no CUDA device: ") + cudaGetErrorString(e)
+                                                         : std::string("device index out of range"));
+        }
+        cudaSetDevice(device);
+        cudaDeviceProp prop;
+        cudaGetDeviceProperties(&prop, device);
+        db->sm_count = prop.multiProcessorCount;
+        if (cudaStreamCreateWithFlags(&db->stream, cudaStreamNonBlocking) != cudaSuccess) {
+            delete db;
+            return fail(PDSAT_ERR_CUDA, "cudaStreamCreate failed");
+        }
+        db->own_stream = true;
+    }
+    static const uint32_t zero_off[1] = {0};
+    if (!db->host.load(n_vars, n_clauses, n_clauses ? offsets : zero_off, lits)) {
+        std::string m = db->host.error;
+        pdsat_destroy(db);
+        return fail(PDSAT_ERR_ARG, m);
+    }
+    int rc = sync_device_db(db);
+    if (rc != PDSAT_OK) {
+        pdsat_destroy(db);
+        return rc;
+    }
+    *out = db;
+    return PDSAT_OK;
+}
+
+int pdsat_set_fixed_assumptions(pdsat_db* db, const int32_t* lits, int32_t n) {
+    if (!db || n < 0 || (n > 0 && !lits)) return fail(PDSAT_ERR_ARG, "pdsat_set_fixed_assumptions: bad argument");
+    if (!db->host.set_fixed(lits, n)) return fail(PDSAT_ERR_ARG, db->host.error);
+    return sync_device_db(db);
+}
+
+int pdsat_db_get_info(const pdsat_db* db, pdsat_db_info* info) {
+    if (!db || !info) return fail(PDSAT_ERR_ARG, "pdsat_db_get_info: bad argument");
+    const HostDb& h = db->host;
+    info->n_vars = h.n_vars;
+    info->n_live_vars = h.n_live;
+    info->n_clauses_in = h.n_clauses_in;
+    info->n_clauses_live = h.n_clauses_live;
+    info->n_lits_live = h.n_lits_live;
+    info->n_base_assigned = h.n_base_assigned;
+    info->max_clause_len = h.max_clause_len;
+    info->status = h.base_ok ? PDSAT_OK : PDSAT_ERR_UNSAT;
+    info->warps_per_cta = db->warps_per_cta;
+    info->smem_bytes = db->smem_bytes;
+    info->grid = db->grid;
+    info->db_in_smem = 0;
+    info->sm_count = db->sm_count;
+    return PDSAT_OK;
+}
+
+int pdsat_db_base_assignment(const pdsat_db* db, uint8_t* assigns) {
+    if (!db || !assigns) return fail(PDSAT_ERR_ARG, "pdsat_db_base_assignment: bad argument");
+    memcpy(assigns, db->host.base_assign.data(), (size_t)db->host.n_vars);
+    return PDSAT_OK;
+}
+
+int pdsat_set_stream(pdsat_db* db, void* cuda_stream) {
+    if (!db) return fail(PDSAT_ERR_ARG, "pdsat_set_stream: null handle");
+    if (db->device < 0) return fail(PDSAT_ERR_CUDA, "host-only handle");
+    if (db->own_stream && db->stream) {
+        cudaStreamSynchronize(db->stream);
+        cudaStreamDestroy(db->stream);
+    }
+    if (cuda_stream) {
+        db->stream = (cudaStream_t)cuda_stream;
+        db->own_stream = false;
+    } else {
+        CU(cudaStreamCreateWithFlags(&db->stream, cudaStreamNonBlocking));
+        db->own_stream = true;
+    }
+    return PDSAT_OK;
+}
+
+void pdsat_destroy(pdsat_db* db) {
+    if (!db) return;
+    if (db->device >= 0) {
+        cudaSetDevice(db->device);
+        free_device_db(db);
+        if (db->own_stream && db->stream) cudaStreamDestroy(db->stream);
+    }
+    delete db;
+}
+
+// ------------------------------------------------------------------------- batches
+static int need_device(const pdsat_db* db) {
+    if (!db) return fail(PDSAT_ERR_ARG, "null database handle");
+    if (db->device < 0) return fail(PDSAT_ERR_CUDA, "host-only handle: no CUDA device bound (there is no CPU fallback)");
+    return PDSAT_OK;
+}
+
+static void mt_plan(HostPoint& hp) {
+    const uint64_t k = hp.set_vars.size();
+    const uint64_t d0 = hp.first_sample * k;
+    hp.mt_first_round = d0 / 624;
+    hp.stream_skip = d0 - hp.mt_first_round * 624;
+    uint64_t bits = hp.stream_skip + hp.n_samples * k;
+    uint64_t rounds = (bits + 623) / 624;
+    rounds += rounds & 1;
+    if (rounds == 0) rounds = 2;
+    hp.mt_rounds = rounds;
+    hp.stream_words = rounds / 2 * 39;
+}
+
+int pdsat_batch_create(pdsat_db* db, int32_t n_points, const pdsat_point* points, uint32_t out_flags,
+                       int32_t max_models, pdsat_batch** out) {
+    int rc = need_device(db);
+    if (rc) return rc;
+    if (!out || n_points <= 0 || !points) return fail(PDSAT_ERR_ARG, "pdsat_batch_create: bad argument");
+    *out = nullptr;
+    const HostDb& h = db->host;
+    pdsat_batch* b = new pdsat_batch();
+    b->db = db;
+    b->out_flags = out_flags;
+    b->max_models = max_models < 0 ? 0 : max_models;
+    b->model_words = (h.n_live + 31) / 32;
+    if (b->model_words == 0) b->model_words = 1;
+    b->pts.resize(n_points);
+    uint64_t groups = 0, words = 0, stream_words = 0;
+    size_t n_codes = 0;
+    std::vector<uint8_t> seen((size_t)h.n_vars);
+    for (int p = 0; p < n_points; p++) {
+        const pdsat_point& in = points[p];
+        HostPoint& hp = b->pts[p];
+        if (in.k <= 0 || !in.set_vars || in.n_samples == 0 || in.mode < 0 || in.mode > 3 ||
+            (in.mode == PDSAT_MODE_EXPLICIT && !in.explicit_values) ||
+            (in.mode == PDSAT_MODE_RANDOM_COUNTER && (in.first_sample & 63))) {
+            delete b;
+            return fail(PDSAT_ERR_ARG, "pdsat_batch_create: bad point " + std::to_string(p));
+        }
+        std::fill(seen.begin(), seen.end(), 0);
+        hp.set_vars.assign(in.set_vars, in.set_vars + in.k);
+        hp.setcode.resize(in.k);
+        hp.n_assumed_live = 0;
+        for (int j = 0; j < in.k; j++) {
+            int32_t v = in.set_vars[j] - 1;
+            if (v < 0 || v >= h.n_vars || seen[v]) {
+                delete b;
+                return fail(PDSAT_ERR_ARG, "pdsat_batch_create: set variable out of range or repeated");
+            }
+            seen[v] = 1;
+            if (h.live_of_var[v] < 0) {
+                hp.setcode[j] = SETCODE_FIXED | (uint32_t)(h.base_assign[v] & 1);
+            } else {
+                hp.setcode[j] = (uint32_t)(2 * h.live_of_var[v]);
+                hp.n_assumed_live++;
+            }
+        }
+        hp.mode = in.mode;
+        hp.seed = in.seed;
+        hp.first_sample = in.first_sample;
+        hp.n_samples = in.n_samples;
+        hp.n_groups = (in.n_samples + 63) / 64;
+        hp.group_start = groups;
+        hp.word_off = words;
+        hp.stream_off = stream_words;
+        groups += hp.n_groups;
+        words += hp.n_groups * (uint64_t)in.k;
+        if (in.mode == PDSAT_MODE_RANDOM_MT19937) {
+            mt_plan(hp);
+            b->n_mt_segs++;
+        } else if (in.mode == PDSAT_MODE_EXPLICIT) {
+            hp.stream_skip = 0;
+            hp.stream_words = (in.n_samples * (uint64_t)in.k + 31) / 32;
+            b->has_explicit = true;
+        }
+        stream_words += hp.stream_words;
+        n_codes += (size_t)in.k;
+    }
+    b->n_groups = groups;
+    b->n_words = words;
+    b->n_stream_words = stream_words;
+
+    auto bail = [&](int code, const std::string& m) {
+        pdsat_batch_destroy(b);
+        return fail(code, m);
+    };
+#define CUB(call)                                                                        \
+    do {                                                                                 \
+        cudaError_t e_ = (call);                                                         \
+        if (e_ != cudaSuccess) return bail(PDSAT_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+    CUB(cudaSetDevice(db->device));
+    CUB(cudaMalloc(&b->d_points, sizeof(PointDev) * n_points));
+    CUB(cudaMallocHost(&b->h_points, sizeof(PointDev) * n_points));
+    CUB(cudaMalloc(&b->d_setcode, sizeof(uint32_t) * n_codes));
+    CUB(cudaMalloc(&b->d_words, sizeof(uint64_t) * words));
+    CUB(cudaMalloc(&b->d_stream, sizeof(uint32_t) * (stream_words ? stream_words : 1)));
+    CUB(cudaMalloc(&b->d_cost, sizeof(unsigned long long) * PDSAT_COST_WORDS * n_points));
+    CUB(cudaMalloc(&b->d_model_count, sizeof(unsigned long long)));
+    if (b->max_models > 0) {
+        CUB(cudaMalloc(&b->d_model_bits, sizeof(uint32_t) * (size_t)b->max_models * b->model_words));
+        CUB(cudaMalloc(&b->d_model_point, sizeof(uint32_t) * b->max_models));
+        CUB(cudaMalloc(&b->d_model_sample, sizeof(uint64_t) * b->max_models));
+    }
+    if (out_flags & PDSAT_OUT_FLAGS) {
+        CUB(cudaMalloc(&b->d_conflict, sizeof(uint64_t) * groups));
+        CUB(cudaMalloc(&b->d_full, sizeof(uint64_t) * groups));
+    }
+    if (out_flags & PDSAT_OUT_TRAIL) CUB(cudaMalloc(&b->d_trail, sizeof(uint16_t) * 64 * groups));
+    if (out_flags & PDSAT_OUT_ASSIGN)
+        CUB(cudaMalloc(&b->d_assign, sizeof(uint64_t) * groups * (size_t)(h.n_live > 0 ? 2 * h.n_live : 1)));
+    if (b->n_mt_segs) {
+        CUB(cudaMalloc(&b->d_mt_states, sizeof(uint32_t) * 624 * b->n_mt_segs));
+        CUB(cudaMalloc(&b->d_mt_segs, sizeof(MtSegment) * b->n_mt_segs));
+        CUB(cudaMallocHost(&b->h_mt_states, sizeof(uint32_t) * 624 * b->n_mt_segs));
+        CUB(cudaMallocHost(&b->h_mt_segs, sizeof(MtSegment) * b->n_mt_segs));
+    }
+    if (b->has_explicit) {
+        CUB(cudaMallocHost(&b->h_stream, sizeof(uint32_t) * stream_words));
+        memset(b->h_stream, 0, sizeof(uint32_t) * stream_words);
+        for (int p = 0; p < n_points; p++) {
+            HostPoint& hp = b->pts[p];
+            if (hp.mode != PDSAT_MODE_EXPLICIT) continue;
+            uint32_t* dst = b->h_stream + hp.stream_off;
+            const uint8_t* src = points[p].explicit_values;
+            const uint64_t nb = hp.n_samples * (uint64_t)hp.set_vars.size();
+            for (uint64_t d = 0; d < nb; d++)
+                if (src[d]) dst[d >> 5] |= 1u << (d & 31);
+        }
+    }
+    {
+        std::vector<uint32_t> codes;
+        codes.reserve(n_codes);
+        uint32_t off = 0;
+        for (int p = 0; p < n_points; p++) {
+            HostPoint& hp = b->pts[p];
+            PointDev& pd = b->h_points[p];
+            pd.n_samples = hp.n_samples;
+            pd.group_start = hp.group_start;
+            pd.word_off = hp.word_off;
+            pd.seed = hp.seed;
+            pd.first_sample = hp.first_sample;
+            pd.stream_off = hp.stream_off;
+            pd.stream_skip = hp.stream_skip;
+            pd.k = (uint32_t)hp.set_vars.size();
+            pd.var_off = off;
+            pd.mode = (uint32_t)hp.mode;
+            pd.n_assumed_live = hp.n_assumed_live;
+            off += pd.k;
+            codes.insert(codes.end(), hp.setcode.begin(), hp.setcode.end());
+        }
+        CUB(cudaMemcpy(b->d_setcode, codes.data(), sizeof(uint32_t) * n_codes, cudaMemcpyHostToDevice));
+        CUB(cudaMemcpy(b->d_points, b->h_points, sizeof(PointDev) * n_points, cudaMemcpyHostToDevice));
+    }
+    for (int i = 0; i < 4; i++) CUB(cudaEventCreate(&b->ev[i]));
+#undef CUB
+    *out = b;
+    return PDSAT_OK;
+}
+
+int pdsat_batch_reseed(pdsat_batch* b, int32_t point, uint64_t seed, uint64_t first_sample) {
+    if (!b || point < 0 || point >= (int)b->pts.size()) return fail(PDSAT_ERR_ARG, "pdsat_batch_reseed: bad argument");
+    HostPoint& hp = b->pts[point];
+    if (hp.mode == PDSAT_MODE_EXPLICIT) return fail(PDSAT_ERR_ARG, "pdsat_batch_reseed: explicit point");
+    if (hp.mode == PDSAT_MODE_RANDOM_COUNTER && (first_sample & 63))
+        return fail(PDSAT_ERR_ARG, "pdsat_batch_reseed: first_sample must be a multiple of 64");
+    hp.seed = seed;
+    if (hp.mode == PDSAT_MODE_RANDOM_MT19937) {
+        // keep the stream buffer size: the new offset must not need more rounds
+        HostPoint t = hp;
+        t.first_sample = first_sample;
+        mt_plan(t);
+        if (t.stream_words > hp.stream_words) return fail(PDSAT_ERR_ARG, "pdsat_batch_reseed: stream window grew");
+        hp.first_sample = first_sample;
+        hp.mt_first_round = t.mt_first_round;
+        hp.stream_skip = t.stream_skip;
+        hp.mt_rounds = t.mt_rounds;
+    } else {
+        hp.first_sample = first_sample;
+    }
+    PointDev& pd = b->h_points[point];
+    pd.seed = hp.seed;
+    pd.first_sample = hp.first_sample;
+    pd.stream_skip = hp.stream_skip;
+    b->filled = false;
+    return PDSAT_OK;
+}
+
+int pdsat_batch_fill(pdsat_batch* b) {
+    if (!b) return fail(PDSAT_ERR_ARG, "pdsat_batch_fill: null batch");
+    pdsat_db* db = b->db;
+    CU(cudaSetDevice(db->device));
+    cudaStream_t st = db->stream;
+    CU(cudaEventRecord(b->ev[0], st));
+    CU(cudaMemcpyAsync(b->d_points, b->h_points, sizeof(PointDev) * b->pts.size(), cudaMemcpyHostToDevice, st));
+    if (b->n_mt_segs) {
+        int s = 0;
+        for (auto& hp : b->pts) {
+            if (hp.mode != PDSAT_MODE_RANDOM_MT19937) continue;
+            mt19937_state_at_round((uint32_t)hp.seed, hp.mt_first_round, b->h_mt_states + (size_t)s * 624);
+            b->h_mt_segs[s].out_off = hp.stream_off;
+            b->h_mt_segs[s].n_rounds = hp.mt_rounds;
+            s++;
+        }
+        CU(cudaMemcpyAsync(b->d_mt_states, b->h_mt_states, sizeof(uint32_t) * 624 * b->n_mt_segs,
+                           cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(b->d_mt_segs, b->h_mt_segs, sizeof(MtSegment) * b->n_mt_segs, cudaMemcpyHostToDevice, st));
+        mt19937_bits_kernel<<<b->n_mt_segs, 256, 0, st>>>(b->d_mt_states, b->d_mt_segs, b->d_stream);
+        b->n_kernels++;
+    }
+    if (b->has_explicit) {
+        for (auto& hp : b->pts) {
+            if (hp.mode != PDSAT_MODE_EXPLICIT) continue;
+            CU(cudaMemcpyAsync(b->d_stream + hp.stream_off, b->h_stream + hp.stream_off,
+                               sizeof(uint32_t) * hp.stream_words, cudaMemcpyHostToDevice, st));
+        }
+    }
+    BatchDev bd{};
+    bd.points = b->d_points;
+    bd.n_points = (int32_t)b->pts.size();
+    bd.n_groups = b->n_groups;
+    bd.n_words = b->n_words;
+    bd.words = b->d_words;
+    bd.stream = b->d_stream;
+    const int threads = 256;
+    const uint64_t blocks = (b->n_words + threads - 1) / threads;
+    fill_words_kernel<<<(unsigned)blocks, threads, 0, st>>>(bd);
+    b->n_kernels++;
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(b->ev[1], st));
+    b->filled = true;
+    return PDSAT_OK;
+}
+
+int pdsat_batch_propagate(pdsat_batch* b) {
+    if (!b) return fail(PDSAT_ERR_ARG, "pdsat_batch_propagate: null batch");
+    if (!b->filled) return fail(PDSAT_ERR_ARG, "pdsat_batch_propagate: batch not filled");
+    pdsat_db* db = b->db;
+    CU(cudaSetDevice(db->device));
+    cudaStream_t st = db->stream;
+    unsigned long long* cost = b->d_cost_ext ? b->d_cost_ext : b->d_cost;
+    CU(cudaEventRecord(b->ev[2], st));
+    CU(cudaMemsetAsync(cost, 0, sizeof(unsigned long long) * PDSAT_COST_WORDS * b->pts.size(), st));
+    CU(cudaMemsetAsync(b->d_model_count, 0, sizeof(unsigned long long), st));
+    BatchDev bd{};
+    bd.points = b->d_points;
+    bd.n_points = (int32_t)b->pts.size();
+    bd.n_groups = b->n_groups;
+    bd.n_words = b->n_words;
+    bd.setcode = b->d_setcode;
+    bd.words = b->d_words;
+    bd.stream = b->d_stream;
+    bd.cost = cost;
+    bd.conflict_bits = b->d_conflict;
+    bd.full_bits = b->d_full;
+    bd.trail = b->d_trail;
+    bd.assign = b->d_assign;
+    bd.model_count = b->d_model_count;
+    bd.model_bits = b->d_model_bits;
+    bd.model_point = b->d_model_point;
+    bd.model_sample = b->d_model_sample;
+    bd.max_models = b->max_models;
+    bd.model_words = b->model_words;
+    uint64_t ctas_needed = (b->n_groups + db->warps_per_cta - 1) / db->warps_per_cta;
+    int grid = (int)(ctas_needed < (uint64_t)db->grid ? ctas_needed : (uint64_t)db->grid);
+    if (grid < 1) grid = 1;
+    bcp_kernel<<<grid, db->warps_per_cta * 32, db->smem_bytes, st>>>(db->dev, bd, db->warp_bytes, db->qcap);
+    b->n_kernels++;
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(b->ev[3], st));
+    b->propagated = true;
+    return PDSAT_OK;
+}
+
+int pdsat_batch_sync(pdsat_batch* b) {
+    if (!b) return fail(PDSAT_ERR_ARG, "pdsat_batch_sync: null batch");
+    CU(cudaStreamSynchronize(b->db->stream));
+    return PDSAT_OK;
+}
+
+int pdsat_batch_last_ms(pdsat_batch* b, float* fill_ms, float* propagate_ms) {
+    if (!b) return fail(PDSAT_ERR_ARG, "pdsat_batch_last_ms: null batch");
+    CU(cudaStreamSynchronize(b->db->stream));
+    if (fill_ms) {
+        *fill_ms = 0;
+        if (b->filled) CU(cudaEventElapsedTime(fill_ms, b->ev[0], b->ev[1]));
+    }
+    if (propagate_ms) {
+        *propagate_ms = 0;
+        if (b->propagated) CU(cudaEventElapsedTime(propagate_ms, b->ev[2], b->ev[3]));
+    }
+    return PDSAT_OK;
+}
+
+int pdsat_batch_launch_count(pdsat_batch* b, int64_t* n_kernels) {
+    if (!b || !n_kernels) return fail(PDSAT_ERR_ARG, "pdsat_batch_launch_count: bad argument");
+    *n_kernels = b->n_kernels;
+    return PDSAT_OK;
+}
+
+int pdsat_batch_cost_device_ptr(pdsat_batch* b, void** dptr) {
+    if (!b || !dptr) return fail(PDSAT_ERR_ARG, "pdsat_batch_cost_device_ptr: bad argument");
+    *dptr = b->d_cost_ext ? b->d_cost_ext : b->d_cost;
+    return PDSAT_OK;
+}
+
+int pdsat_batch_set_cost_buffer(pdsat_batch* b, void* dptr) {
+    if (!b) return fail(PDSAT_ERR_ARG, "pdsat_batch_set_cost_buffer: null batch");
+    b->d_cost_ext = (unsigned long long*)dptr;
+    return PDSAT_OK;
+}
+
+int pdsat_batch_costs(pdsat_batch* b, pdsat_cost* out) {
+    if (!b || !out) return fail(PDSAT_ERR_ARG, "pdsat_batch_costs: bad argument");
+    if (!b->propagated) return fail(PDSAT_ERR_ARG, "pdsat_batch_costs: batch not propagated");
+    static_assert(sizeof(pdsat_cost) == 8 * PDSAT_COST_WORDS, "pdsat_cost layout");
+    unsigned long long* cost = b->d_cost_ext ? b->d_cost_ext : b->d_cost;
+    CU(cudaMemcpyAsync(out, cost, sizeof(pdsat_cost) * b->pts.size(), cudaMemcpyDeviceToHost, b->db->stream));
+    CU(cudaStreamSynchronize(b->db->stream));
+    return PDSAT_OK;
+}
+
+int pdsat_batch_flags(pdsat_batch* b, int32_t point, uint64_t* conflict_bits, uint64_t* full_bits) {
+    if (!b || point < 0 || point >= (int)b->pts.size()) return fail(PDSAT_ERR_ARG, "pdsat_batch_flags: bad argument");
+    if (!b->d_conflict || !b->propagated) return fail(PDSAT_ERR_ARG, "pdsat_batch_flags: PDSAT_OUT_FLAGS not requested / not run");
+    const HostPoint& hp = b->pts[point];
+    CU(cudaStreamSynchronize(b->db->stream));
+    if (conflict_bits)
+        CU(cudaMemcpy(conflict_bits, b->d_conflict + hp.group_start, sizeof(uint64_t) * hp.n_groups, cudaMemcpyDeviceToHost));
+    if (full_bits)
+        CU(cudaMemcpy(full_bits, b->d_full + hp.group_start, sizeof(uint64_t) * hp.n_groups, cudaMemcpyDeviceToHost));
+    return PDSAT_OK;
+}
+
+int pdsat_batch_trail(pdsat_batch* b, int32_t point, uint16_t* trail) {
+    if (!b || !trail || point < 0 || point >= (int)b->pts.size()) return fail(PDSAT_ERR_ARG, "pdsat_batch_trail: bad argument");
+    if (!b->d_trail || !b->propagated) return fail(PDSAT_ERR_ARG, "pdsat_batch_trail: PDSAT_OUT_TRAIL not requested / not run");
+    const HostPoint& hp = b->pts[point];
+    CU(cudaStreamSynchronize(b->db->stream));
+    CU(cudaMemcpy(trail, b->d_trail + hp.group_start * 64, sizeof(uint16_t) * hp.n_samples, cudaMemcpyDeviceToHost));
+    return PDSAT_OK;
+}
+
+int pdsat_batch_assign(pdsat_batch* b, int32_t point, uint64_t first, uint64_t n, uint8_t* assigns) {
+    if (!b || !assigns || point < 0 || point >= (int)b->pts.size()) return fail(PDSAT_ERR_ARG, "pdsat_batch_assign: bad argument");
+    if (!b->d_assign || !b->propagated) return fail(PDSAT_ERR_ARG, "pdsat_batch_assign: PDSAT_OUT_ASSIGN not requested / not run");
+    const HostPoint& hp = b->pts[point];
+    if (first + n > hp.n_samples) return fail(PDSAT_ERR_ARG, "pdsat_batch_assign: range");
+    const HostDb& h = b->db->host;
+    const size_t n_lit = (size_t)2 * h.n_live;
+    CU(cudaStreamSynchronize(b->db->stream));
+    std::vector<uint64_t> planes(n_lit ? n_lit : 1);
+    uint64_t cur_group = ~0ull;
+    for (uint64_t s = first; s < first + n; s++) {
+        uint64_t g = s / 64;
+        if (g != cur_group) {
+            if (n_lit)
+                CU(cudaMemcpy(planes.data(), b->d_assign + (hp.group_start + g) * n_lit, sizeof(uint64_t) * n_lit,
+                              cudaMemcpyDeviceToHost));
+            cur_group = g;
+        }
+        uint8_t* dst = assigns + (s - first) * (size_t)h.n_vars;
+        memcpy(dst, h.base_assign.data(), (size_t)h.n_vars);
+        const int bit = (int)(s & 63);
+        for (int lv = 0; lv < h.n_live; lv++) {
+            const bool t = (planes[2 * lv] >> bit) & 1, f = (planes[2 * lv + 1] >> bit) & 1;
+            dst[h.var_of_live[lv]] = t ? LB_TRUE : (f ? LB_FALSE : LB_UNDEF);
+        }
+    }
+    return PDSAT_OK;
+}
+
+int pdsat_batch_models(pdsat_batch* b, int64_t* n_found, int32_t* point_of, uint64_t* sample_of, uint8_t* models) {
+    if (!b || !n_found) return fail(PDSAT_ERR_ARG, "pdsat_batch_models: bad argument");
+    if (!b->propagated) return fail(PDSAT_ERR_ARG, "pdsat_batch_models: batch not propagated");
+    CU(cudaStreamSynchronize(b->db->stream));
+    unsigned long long cnt = 0;
+    CU(cudaMemcpy(&cnt, b->d_model_count, sizeof(cnt), cudaMemcpyDeviceToHost));
+    *n_found = (int64_t)cnt;
+    const int64_t stored = (int64_t)cnt < b->max_models ? (int64_t)cnt : b->max_models;
+    if (stored == 0) return PDSAT_OK;
+    const HostDb& h = b->db->host;
+    std::vector<uint32_t> bits((size_t)stored * b->model_words), pts((size_t)stored);
+    std::vector<uint64_t> smp((size_t)stored);
+    CU(cudaMemcpy(bits.data(), b->d_model_bits, sizeof(uint32_t) * bits.size(), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(pts.data(), b->d_model_point, sizeof(uint32_t) * stored, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(smp.data(), b->d_model_sample, sizeof(uint64_t) * stored, cudaMemcpyDeviceToHost));
+    for (int64_t i = 0; i < stored; i++) {
+        if (point_of) point_of[i] = (int32_t)pts[i];
+        if (sample_of) sample_of[i] = smp[i];
+        if (models) {
+            uint8_t* dst = models + (size_t)i * h.n_vars;
+            for (int v = 0; v < h.n_vars; v++) dst[v] = h.base_assign[v] == LB_TRUE ? 1 : 0;
+            for (int lv = 0; lv < h.n_live; lv++)
+                dst[h.var_of_live[lv]] = (bits[(size_t)i * b->model_words + (lv >> 5)] >> (lv & 31)) & 1u;
+        }
+    }
+    return PDSAT_OK;
+}
+
+void pdsat_batch_destroy(pdsat_batch* b) {
+    if (!b) return;
+    if (b->db && b->db->device >= 0) {
+        cudaSetDevice(b->db->device);
+        if (b->db->stream) cudaStreamSynchronize(b->db->stream);
+    }
+    cudaFree(b->d_points);
+    cudaFree(b->d_setcode);
+    cudaFree(b->d_words);
+    cudaFree(b->d_stream);
+    cudaFree(b->d_cost);
+    cudaFree(b->d_conflict);
+    cudaFree(b->d_full);
+    cudaFree(b->d_trail);
+    cudaFree(b->d_assign);
+    cudaFree(b->d_model_count);
+    cudaFree(b->d_model_bits);
+    cudaFree(b->d_model_point);
+    cudaFree(b->d_model_sample);
+    cudaFree(b->d_mt_states);
+    cudaFree(b->d_mt_segs);
+    if (b->h_mt_states) cudaFreeHost(b->h_mt_states);
+    if (b->h_mt_segs) cudaFreeHost(b->h_mt_segs);
+    if (b->h_stream) cudaFreeHost(b->h_stream);
+    if (b->h_points) cudaFreeHost(b->h_points);
+    for (int i = 0; i < 4; i++)
+        if (b->ev[i]) cudaEventDestroy(b->ev[i]);
+    delete b;
+}
+
+int pdsat_eval_batch(pdsat_db* db, int32_t n_points, const pdsat_point* points, pdsat_cost* costs) {
+    if (!costs) return fail(PDSAT_ERR_ARG, "pdsat_eval_batch: null costs");
+    pdsat_batch* b = nullptr;
+    int rc = pdsat_batch_create(db, n_points, points, 0, 0, &b);
+    if (rc) return rc;
+    rc = pdsat_batch_fill(b);
+    if (!rc) rc = pdsat_batch_propagate(b);
+    if (!rc) rc = pdsat_batch_costs(b, costs);
+    std::string keep = g_err;
+    pdsat_batch_destroy(b);
+    if (rc) g_err = keep;
+    return rc;
+}
+
+int pdsat_mt19937_bool_rand(int device, uint32_t seed, uint64_t first, uint64_t n, uint8_t* out) {
+    if (!out) return fail(PDSAT_ERR_ARG, "pdsat_mt19937_bool_rand: null out");
+    int cnt = 0;
+    if (cudaGetDeviceCount(&cnt) != cudaSuccess || device < 0 || device >= cnt)
+        return fail(PDSAT_ERR_CUDA, "no CUDA device (there is no CPU fallback)");
+    CU(cudaSetDevice(device));
+    const uint64_t r0 = first / 624, skip = first - r0 * 624;
+    uint64_t rounds = (skip + n + 623) / 624;
+    rounds += rounds & 1;
+    if (!rounds) rounds = 2;
+    const uint64_t words = rounds / 2 * 39;
+    std::vector<uint32_t> state(624), hbits(words);
+    mt19937_state_at_round(seed, r0, state.data());
+    MtSegment seg{0, rounds};
+    uint32_t *d_state = nullptr, *d_out = nullptr;
+    MtSegment* d_seg = nullptr;
+    CU(cudaMalloc(&d_state, 624 * 4));
+    CU(cudaMalloc(&d_seg, sizeof(seg)));
+    CU(cudaMalloc(&d_out, words * 4));
+    CU(cudaMemcpy(d_state, state.data(), 624 * 4, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(d_seg, &seg, sizeof(seg), cudaMemcpyHostToDevice));
+    mt19937_bits_kernel<<<1, 256>>>(d_state, d_seg, d_out);
+    CU(cudaGetLastError());
+    CU(cudaMemcpy(hbits.data(), d_out, words * 4, cudaMemcpyDeviceToHost));
+    cudaFree(d_state);
+    cudaFree(d_seg);
+    cudaFree(d_out);
+    for (uint64_t i = 0; i < n; i++) {
+        uint64_t d = skip + i;
+        out[i] = (hbits[d >> 5] >> (d & 31)) & 1u;
+    }
+    return PDSAT_OK;
+}
+
+}  // extern "C"
