@@ -227,7 +227,10 @@ def run_ours(args):
     nv, cl, offs, lits, stream = instance()
     db = api.ClauseDb(nv, offs, lits, device=local_rank)
     db.set_fixed_assumptions(stream)
-    stream_t = torch.cuda.current_stream()
+    # run the library on a torch-owned (non-default) stream so that torch.cuda.Event pairs
+    # recorded below sit on the stream the kernels are launched on
+    stream_t = torch.cuda.Stream()
+    torch.cuda.set_stream(stream_t)
     db.set_stream(stream_t.cuda_stream)
     n = args.samples
     seed0 = 1 + rank  # the reference seeds each worker's generator with its rank
