@@ -126,11 +126,69 @@ __global__ void fill_words_kernel(BatchDev b) {
 struct MtSegment {
     uint64_t out_off;   // 32-bit word offset of this segment's first output bit (round aligned)
     uint64_t n_rounds;  // rounds of 624 draws to produce (always even)
+    uint32_t state_idx; // slot of the generator state that precedes the first round
+    uint32_t pad;
 };
 
-// One CTA (256 threads) per stream segment.  state[seg] is the 624-word generator state
-// *before* the twist that produces the segment's first round.  Emits, per draw, the
-// bool_rand bit ((tempered >> 31) == 0), packed little-endian into 32-bit words.
+// One jump-ahead: states[dst] = g(A) states[src], g = polys[poly] (x^(624*2^t) mod phi as
+// 19968 bits).  out[w] = XOR over the set bits i of g of x[i + w], where x[0..623] is the
+// source window and x continues by the mt19937 recurrence (mt_jump.hpp).
+struct MtJumpTask {
+    uint32_t src, dst, poly, pad;
+};
+
+static constexpr int MT_JUMP_THREADS = 640;
+static constexpr int MT_JUMP_ROUNDS = 33;  // 33 * 624 = 20592 >= 19937 + 623 words
+static constexpr int MT_JUMP_SMEM = (MT_JUMP_ROUNDS * 624 + 624) * 4;
+
+__global__ void __launch_bounds__(MT_JUMP_THREADS) mt19937_jump_kernel(const uint32_t* __restrict__ polys,
+                                                                       uint32_t* __restrict__ states,
+                                                                       const MtJumpTask* __restrict__ tasks) {
+    extern __shared__ uint32_t jsm[];
+    uint32_t* x = jsm;                         // MT_JUMP_ROUNDS * 624 words of the sequence
+    uint32_t* g = jsm + MT_JUMP_ROUNDS * 624;  // 624 words of polynomial bits
+    const int tid = threadIdx.x;
+    const MtJumpTask t = tasks[blockIdx.x];
+    const uint32_t* src = states + (size_t)t.src * 624;
+    const uint32_t* gp = polys + (size_t)t.poly * 624;
+    if (tid < 624) {
+        x[tid] = src[tid];
+        g[tid] = gp[tid];
+    }
+    __syncthreads();
+    // run the recurrence forward: x[n+624] = x[n+397] ^ twist(x[n], x[n+1])
+    for (int r = 0; r < MT_JUMP_ROUNDS - 1; r++) {
+        uint32_t* cur = x + r * 624;
+        const int base[3] = {0, 227, 454};
+        const int cnt[3] = {227, 227, 170};
+#pragma unroll
+        for (int ph = 0; ph < 3; ph++) {
+            if (tid < cnt[ph]) {
+                const int n = base[ph] + tid;
+                const uint32_t y = (cur[n] & 0x80000000u) | (cur[n + 1] & 0x7fffffffu);
+                cur[n + 624] = cur[n + 397] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+            }
+            __syncthreads();
+        }
+    }
+    if (tid < 624) {
+        uint32_t acc = 0;
+        for (int c = 0; c < 624; c++) {
+            uint32_t gw = g[c];
+            const uint32_t* xb = x + c * 32 + tid;
+            while (gw) {
+                const int b = __ffs(gw) - 1;
+                gw &= gw - 1;
+                acc ^= xb[b];
+            }
+        }
+        states[(size_t)t.dst * 624 + tid] = acc;
+    }
+}
+
+// One CTA (256 threads) per stream segment.  states[state_base + blockIdx.x] is the 624-word
+// generator state *before* the twist that produces the segment's first round.  Emits, per
+// draw, the bool_rand bit ((tempered >> 31) == 0), packed little-endian into 32-bit words.
 __global__ void __launch_bounds__(256) mt19937_bits_kernel(const uint32_t* __restrict__ states,
                                                            const MtSegment* __restrict__ segs,
                                                            uint32_t* __restrict__ out) {
@@ -138,7 +196,7 @@ __global__ void __launch_bounds__(256) mt19937_bits_kernel(const uint32_t* __res
     __shared__ uint32_t pairw[40];
     const int tid = threadIdx.x;
     const MtSegment seg = segs[blockIdx.x];
-    const uint32_t* s0 = states + (size_t)blockIdx.x * 624;
+    const uint32_t* s0 = states + (size_t)seg.state_idx * 624;
     for (int i = tid; i < 624; i += 256) st[i] = s0[i];
     if (tid < 40) pairw[tid] = 0;
     __syncthreads();

@@ -40,7 +40,11 @@ struct pdsat_db {
     DbDev dev{};
     // launch shape
     int warps_per_cta = 0, warp_bytes = 0, qcap = 0, smem_bytes = 0, grid = 0;
+    // mt19937 jump polynomials x^(624*2^t) mod phi resident on the device (lazy)
+    uint32_t* d_polys = nullptr;
+    int n_polys = 0;
 };
+static constexpr int MAX_POLYS = 64;
 
 struct HostPoint {
     std::vector<int32_t> set_vars;
@@ -50,6 +54,11 @@ struct HostPoint {
     uint64_t n_groups = 0, group_start = 0, word_off = 0, stream_off = 0, stream_skip = 0, stream_words = 0;
     uint64_t mt_first_round = 0, mt_rounds = 0;
     uint32_t n_assumed_live = 0;
+    // mt19937 stream segments of 2^mt_m rounds each
+    uint32_t mt_index = 0;      // index among the batch's mt19937 points (= state slot of segment 0)
+    uint32_t n_segs = 0;
+    uint32_t extra_base = 0;    // state slot of segment 1
+    uint64_t seg_base = 0;      // global index of segment 0
 };
 
 struct pdsat_batch {
@@ -77,9 +86,15 @@ struct pdsat_batch {
     // mt19937 segments
     uint32_t* d_mt_states = nullptr;
     MtSegment* d_mt_segs = nullptr;
-    uint32_t* h_mt_states = nullptr;  // pinned
+    uint32_t* h_mt_states = nullptr;  // pinned: seed states of the mt19937 points
     MtSegment* h_mt_segs = nullptr;   // pinned
+    MtJumpTask* d_mt_tasks = nullptr;
+    MtJumpTask* h_mt_tasks = nullptr; // pinned
+    size_t mt_tasks_cap = 0;
+    int n_mt_points = 0;
     int n_mt_segs = 0;
+    int mt_m = 1;                     // log2(rounds per segment)
+    size_t n_mt_states = 0;
     // explicit values, packed on the host (pinned)
     uint32_t* h_stream = nullptr;
     bool has_explicit = false;
@@ -261,6 +276,7 @@ void pdsat_destroy(pdsat_db* db) {
     if (db->device >= 0) {
         cudaSetDevice(db->device);
         free_device_db(db);
+        cudaFree(db->d_polys);
         if (db->own_stream && db->stream) cudaStreamDestroy(db->stream);
     }
     delete db;
@@ -273,17 +289,20 @@ static int need_device(const pdsat_db* db) {
     return PDSAT_OK;
 }
 
+// position of a point's sample window inside its mt19937 stream
 static void mt_plan(HostPoint& hp) {
     const uint64_t k = hp.set_vars.size();
     const uint64_t d0 = hp.first_sample * k;
     hp.mt_first_round = d0 / 624;
     hp.stream_skip = d0 - hp.mt_first_round * 624;
-    uint64_t bits = hp.stream_skip + hp.n_samples * k;
-    uint64_t rounds = (bits + 623) / 624;
-    rounds += rounds & 1;
-    if (rounds == 0) rounds = 2;
-    hp.mt_rounds = rounds;
-    hp.stream_words = rounds / 2 * 39;
+    // rounds to allocate: worst-case skip (623), so that a reseed never needs more
+    hp.mt_rounds = (623 + hp.n_samples * k + 623) / 624;
+}
+
+static int mt_target_segments() {
+    const char* e = getenv("PDSAT_MT_SEGMENTS");
+    int t = e ? atoi(e) : 0;
+    return t > 0 ? t : 592;  // 4 CTAs per SM on a 148-SM part
 }
 
 int pdsat_batch_create(pdsat_db* db, int32_t n_points, const pdsat_point* points, uint32_t out_flags,
@@ -337,19 +356,44 @@ int pdsat_batch_create(pdsat_db* db, int32_t n_points, const pdsat_point* points
         hp.n_groups = (in.n_samples + 63) / 64;
         hp.group_start = groups;
         hp.word_off = words;
-        hp.stream_off = stream_words;
         groups += hp.n_groups;
         words += hp.n_groups * (uint64_t)in.k;
         if (in.mode == PDSAT_MODE_RANDOM_MT19937) {
             mt_plan(hp);
-            b->n_mt_segs++;
+            hp.mt_index = (uint32_t)b->n_mt_points++;
         } else if (in.mode == PDSAT_MODE_EXPLICIT) {
             hp.stream_skip = 0;
             hp.stream_words = (in.n_samples * (uint64_t)in.k + 31) / 32;
             b->has_explicit = true;
         }
-        stream_words += hp.stream_words;
         n_codes += (size_t)in.k;
+    }
+    // mt19937 streams are cut into segments of 2^m rounds (m >= 1) generated by one CTA each
+    if (b->n_mt_points) {
+        uint64_t total_rounds = 0;
+        for (auto& hp : b->pts)
+            if (hp.mode == PDSAT_MODE_RANDOM_MT19937) total_rounds += hp.mt_rounds;
+        const uint64_t per_seg = (total_rounds + mt_target_segments() - 1) / mt_target_segments();
+        int m = 1;
+        while ((1ull << m) < per_seg) m++;
+        b->mt_m = m;
+        uint32_t extra = (uint32_t)b->n_mt_points;
+        uint64_t seg = 0;
+        for (auto& hp : b->pts) {
+            if (hp.mode != PDSAT_MODE_RANDOM_MT19937) continue;
+            hp.n_segs = (uint32_t)((hp.mt_rounds + (1ull << m) - 1) >> m);
+            hp.extra_base = extra;
+            extra += hp.n_segs - 1;
+            hp.seg_base = seg;
+            seg += hp.n_segs;
+            hp.stream_words = (uint64_t)hp.n_segs * ((1ull << m) / 2) * 39;
+        }
+        b->n_mt_segs = (int)seg;
+        b->n_mt_states = extra;
+    }
+    for (auto& hp : b->pts) {
+        hp.stream_off = stream_words;
+        stream_words += hp.stream_words;
     }
     b->n_groups = groups;
     b->n_words = words;
@@ -385,10 +429,25 @@ int pdsat_batch_create(pdsat_db* db, int32_t n_points, const pdsat_point* points
     if (out_flags & PDSAT_OUT_ASSIGN)
         CUB(cudaMalloc(&b->d_assign, sizeof(uint64_t) * groups * (size_t)(h.n_live > 0 ? 2 * h.n_live : 1)));
     if (b->n_mt_segs) {
-        CUB(cudaMalloc(&b->d_mt_states, sizeof(uint32_t) * 624 * b->n_mt_segs));
+        CUB(cudaMalloc(&b->d_mt_states, sizeof(uint32_t) * 624 * b->n_mt_states));
         CUB(cudaMalloc(&b->d_mt_segs, sizeof(MtSegment) * b->n_mt_segs));
-        CUB(cudaMallocHost(&b->h_mt_states, sizeof(uint32_t) * 624 * b->n_mt_segs));
+        CUB(cudaMallocHost(&b->h_mt_states, sizeof(uint32_t) * 624 * b->n_mt_points));
         CUB(cudaMallocHost(&b->h_mt_segs, sizeof(MtSegment) * b->n_mt_segs));
+        b->mt_tasks_cap = (size_t)b->n_mt_segs + 64 * (size_t)b->n_mt_points;
+        CUB(cudaMalloc(&b->d_mt_tasks, sizeof(MtJumpTask) * b->mt_tasks_cap));
+        CUB(cudaMallocHost(&b->h_mt_tasks, sizeof(MtJumpTask) * b->mt_tasks_cap));
+        for (auto& hp : b->pts) {
+            if (hp.mode != PDSAT_MODE_RANDOM_MT19937) continue;
+            for (uint32_t j = 0; j < hp.n_segs; j++) {
+                MtSegment& sg = b->h_mt_segs[hp.seg_base + j];
+                sg.out_off = hp.stream_off + (uint64_t)j * ((1ull << b->mt_m) / 2) * 39;
+                sg.n_rounds = 1ull << b->mt_m;
+                sg.state_idx = j == 0 ? hp.mt_index : hp.extra_base + j - 1;
+                sg.pad = 0;
+            }
+        }
+        CUB(cudaMemcpy(b->d_mt_segs, b->h_mt_segs, sizeof(MtSegment) * b->n_mt_segs, cudaMemcpyHostToDevice));
+        CUB(cudaFuncSetAttribute(mt19937_jump_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MT_JUMP_SMEM));
     }
     if (b->has_explicit) {
         CUB(cudaMallocHost(&b->h_stream, sizeof(uint32_t) * stream_words));
@@ -441,15 +500,8 @@ int pdsat_batch_reseed(pdsat_batch* b, int32_t point, uint64_t seed, uint64_t fi
         return fail(PDSAT_ERR_ARG, "pdsat_batch_reseed: first_sample must be a multiple of 64");
     hp.seed = seed;
     if (hp.mode == PDSAT_MODE_RANDOM_MT19937) {
-        // keep the stream buffer size: the new offset must not need more rounds
-        HostPoint t = hp;
-        t.first_sample = first_sample;
-        mt_plan(t);
-        if (t.stream_words > hp.stream_words) return fail(PDSAT_ERR_ARG, "pdsat_batch_reseed: stream window grew");
         hp.first_sample = first_sample;
-        hp.mt_first_round = t.mt_first_round;
-        hp.stream_skip = t.stream_skip;
-        hp.mt_rounds = t.mt_rounds;
+        mt_plan(hp);  // the allocation already covers the worst-case skip
     } else {
         hp.first_sample = first_sample;
     }
@@ -469,17 +521,67 @@ int pdsat_batch_fill(pdsat_batch* b) {
     CU(cudaEventRecord(b->ev[0], st));
     CU(cudaMemcpyAsync(b->d_points, b->h_points, sizeof(PointDev) * b->pts.size(), cudaMemcpyHostToDevice, st));
     if (b->n_mt_segs) {
-        int s = 0;
+        // seed states -> slot mt_index; jump-ahead (mt_jump.hpp) places every other segment
+        int max_poly = -1;
         for (auto& hp : b->pts) {
             if (hp.mode != PDSAT_MODE_RANDOM_MT19937) continue;
-            mt19937_state_at_round((uint32_t)hp.seed, hp.mt_first_round, b->h_mt_states + (size_t)s * 624);
-            b->h_mt_segs[s].out_off = hp.stream_off;
-            b->h_mt_segs[s].n_rounds = hp.mt_rounds;
-            s++;
+            mt19937_seed((uint32_t)hp.seed, b->h_mt_states + (size_t)hp.mt_index * 624);
         }
-        CU(cudaMemcpyAsync(b->d_mt_states, b->h_mt_states, sizeof(uint32_t) * 624 * b->n_mt_segs,
+        CU(cudaMemcpyAsync(b->d_mt_states, b->h_mt_states, sizeof(uint32_t) * 624 * b->n_mt_points,
                            cudaMemcpyHostToDevice, st));
-        CU(cudaMemcpyAsync(b->d_mt_segs, b->h_mt_segs, sizeof(MtSegment) * b->n_mt_segs, cudaMemcpyHostToDevice, st));
+        // launch plan: (a) per set bit t of the first round, in-place jumps by 2^t rounds;
+        // (b) binary tree over the segments, top level first
+        struct Launch { size_t off, cnt; };
+        std::vector<Launch> launches;
+        size_t nt = 0;
+        for (int t = 0; t < 64; t++) {
+            size_t start = nt;
+            for (auto& hp : b->pts) {
+                if (hp.mode != PDSAT_MODE_RANDOM_MT19937 || !((hp.mt_first_round >> t) & 1ull)) continue;
+                b->h_mt_tasks[nt++] = MtJumpTask{hp.mt_index, hp.mt_index, (uint32_t)t, 0};
+            }
+            if (nt > start) {
+                launches.push_back({start, nt - start});
+                if (t > max_poly) max_poly = t;
+            }
+        }
+        uint32_t max_segs = 0;
+        for (auto& hp : b->pts)
+            if (hp.mode == PDSAT_MODE_RANDOM_MT19937 && hp.n_segs > max_segs) max_segs = hp.n_segs;
+        int top = 0;
+        while ((2u << top) < max_segs) top++;
+        for (int lev = top; lev >= 0 && max_segs > 1; lev--) {
+            size_t start = nt;
+            const uint32_t stride = 1u << lev;
+            for (auto& hp : b->pts) {
+                if (hp.mode != PDSAT_MODE_RANDOM_MT19937) continue;
+                for (uint32_t j = 0; j + stride < hp.n_segs; j += 2 * stride) {
+                    const uint32_t src = j == 0 ? hp.mt_index : hp.extra_base + j - 1;
+                    const uint32_t dst = hp.extra_base + j + stride - 1;
+                    b->h_mt_tasks[nt++] = MtJumpTask{src, dst, (uint32_t)(b->mt_m + lev), 0};
+                }
+            }
+            if (nt > start) {
+                launches.push_back({start, nt - start});
+                if (b->mt_m + lev > max_poly) max_poly = b->mt_m + lev;
+            }
+        }
+        if (max_poly >= MAX_POLYS) return fail(PDSAT_ERR_LIMIT, "mt19937 stream offset too large");
+        if (max_poly >= 0) {
+            if (!db->d_polys) CU(cudaMalloc(&db->d_polys, sizeof(uint32_t) * 624 * MAX_POLYS));
+            while (db->n_polys <= max_poly) {
+                const uint32_t* pl = MtJumpPolys::instance().poly(db->n_polys);
+                CU(cudaMemcpyAsync(db->d_polys + (size_t)db->n_polys * 624, pl, sizeof(uint32_t) * 624,
+                                   cudaMemcpyHostToDevice, st));
+                db->n_polys++;
+            }
+            CU(cudaMemcpyAsync(b->d_mt_tasks, b->h_mt_tasks, sizeof(MtJumpTask) * nt, cudaMemcpyHostToDevice, st));
+            for (auto& L : launches) {
+                mt19937_jump_kernel<<<(unsigned)L.cnt, MT_JUMP_THREADS, MT_JUMP_SMEM, st>>>(db->d_polys, b->d_mt_states,
+                                                                                             b->d_mt_tasks + L.off);
+                b->n_kernels++;
+            }
+        }
         mt19937_bits_kernel<<<b->n_mt_segs, 256, 0, st>>>(b->d_mt_states, b->d_mt_segs, b->d_stream);
         b->n_kernels++;
     }
@@ -694,6 +796,8 @@ void pdsat_batch_destroy(pdsat_batch* b) {
     cudaFree(b->d_model_sample);
     cudaFree(b->d_mt_states);
     cudaFree(b->d_mt_segs);
+    cudaFree(b->d_mt_tasks);
+    if (b->h_mt_tasks) cudaFreeHost(b->h_mt_tasks);
     if (b->h_mt_states) cudaFreeHost(b->h_mt_states);
     if (b->h_mt_segs) cudaFreeHost(b->h_mt_segs);
     if (b->h_stream) cudaFreeHost(b->h_stream);
@@ -723,27 +827,59 @@ int pdsat_mt19937_bool_rand(int device, uint32_t seed, uint64_t first, uint64_t 
     if (cudaGetDeviceCount(&cnt) != cudaSuccess || device < 0 || device >= cnt)
         return fail(PDSAT_ERR_CUDA, "no CUDA device (there is no CPU fallback)");
     CU(cudaSetDevice(device));
+    // same machinery as a batch: seed state, jump to round r0 (one in-place jump per set
+    // bit), split the window into 4 segments by tree jumps, emit the bits
     const uint64_t r0 = first / 624, skip = first - r0 * 624;
-    uint64_t rounds = (skip + n + 623) / 624;
-    rounds += rounds & 1;
-    if (!rounds) rounds = 2;
-    const uint64_t words = rounds / 2 * 39;
+    const uint64_t need = (skip + n + 623) / 624;
+    int m = 1;
+    while ((4ull << m) < need) m++;
+    const uint64_t L = 1ull << m;
+    const int n_segs = 4;
+    const uint64_t words = n_segs * (L / 2) * 39;
     std::vector<uint32_t> state(624), hbits(words);
-    mt19937_state_at_round(seed, r0, state.data());
-    MtSegment seg{0, rounds};
-    uint32_t *d_state = nullptr, *d_out = nullptr;
+    mt19937_seed(seed, state.data());
+    std::vector<MtJumpTask> tasks;
+    std::vector<std::pair<size_t, size_t>> launches;
+    int max_poly = -1;
+    for (int t = 0; t < 64; t++)
+        if ((r0 >> t) & 1ull) {
+            launches.push_back({tasks.size(), 1});
+            tasks.push_back(MtJumpTask{0, 0, (uint32_t)t, 0});
+            max_poly = t;
+        }
+    launches.push_back({tasks.size(), 1});
+    tasks.push_back(MtJumpTask{0, 2, (uint32_t)(m + 1), 0});
+    launches.push_back({tasks.size(), 2});
+    tasks.push_back(MtJumpTask{0, 1, (uint32_t)m, 0});
+    tasks.push_back(MtJumpTask{2, 3, (uint32_t)m, 0});
+    if (m + 1 > max_poly) max_poly = m + 1;
+    if (max_poly >= MAX_POLYS) return fail(PDSAT_ERR_LIMIT, "mt19937 stream offset too large");
+    std::vector<MtSegment> segs(n_segs);
+    for (int j = 0; j < n_segs; j++) segs[j] = MtSegment{(uint64_t)j * (L / 2) * 39, L, (uint32_t)j, 0};
+    uint32_t *d_state = nullptr, *d_out = nullptr, *d_polys = nullptr;
     MtSegment* d_seg = nullptr;
-    CU(cudaMalloc(&d_state, 624 * 4));
-    CU(cudaMalloc(&d_seg, sizeof(seg)));
+    MtJumpTask* d_tasks = nullptr;
+    CU(cudaMalloc(&d_state, 624 * 4 * n_segs));
+    CU(cudaMalloc(&d_seg, sizeof(MtSegment) * n_segs));
     CU(cudaMalloc(&d_out, words * 4));
+    CU(cudaMalloc(&d_polys, (size_t)(max_poly + 1) * 624 * 4));
+    CU(cudaMalloc(&d_tasks, sizeof(MtJumpTask) * tasks.size()));
+    for (int t = 0; t <= max_poly; t++)
+        CU(cudaMemcpy(d_polys + (size_t)t * 624, MtJumpPolys::instance().poly(t), 624 * 4, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(d_state, state.data(), 624 * 4, cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(d_seg, &seg, sizeof(seg), cudaMemcpyHostToDevice));
-    mt19937_bits_kernel<<<1, 256>>>(d_state, d_seg, d_out);
+    CU(cudaMemcpy(d_seg, segs.data(), sizeof(MtSegment) * n_segs, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(d_tasks, tasks.data(), sizeof(MtJumpTask) * tasks.size(), cudaMemcpyHostToDevice));
+    CU(cudaFuncSetAttribute(mt19937_jump_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MT_JUMP_SMEM));
+    for (auto& l : launches)
+        mt19937_jump_kernel<<<(unsigned)l.second, MT_JUMP_THREADS, MT_JUMP_SMEM>>>(d_polys, d_state, d_tasks + l.first);
+    mt19937_bits_kernel<<<n_segs, 256>>>(d_state, d_seg, d_out);
     CU(cudaGetLastError());
     CU(cudaMemcpy(hbits.data(), d_out, words * 4, cudaMemcpyDeviceToHost));
     cudaFree(d_state);
     cudaFree(d_seg);
     cudaFree(d_out);
+    cudaFree(d_polys);
+    cudaFree(d_tasks);
     for (uint64_t i = 0; i < n; i++) {
         uint64_t d = skip + i;
         out[i] = (hbits[d >> 5] >> (d & 31)) & 1u;

@@ -210,7 +210,8 @@ def test_gpu_enum_mode_small_cnf(oracle_mod, cuda_lib):
 
 def test_gpu_mt19937_stream(oracle_mod, cuda_lib):
     from pdsat_b200 import api
-    for seed, first, n in [(1, 0, 5000), (5489, 9990, 20), (7, 623, 1300), (0, 1248, 1248)]:
+    for seed, first, n in [(1, 0, 5000), (5489, 9990, 20), (7, 623, 1300), (0, 1248, 1248),
+                           (3, 624 * 1000 + 17, 70000), (11, 150_000_007, 4000)]:
         got = api.mt19937_bool_rand(seed, first, n)
         exp = oracle_mod.bool_rand(seed, first, n)
         assert (got == exp).all(), (seed, first, n)
@@ -250,3 +251,31 @@ def test_gpu_counter_mode_declared_generator(bivium, golden, oracle_mod, cuda_li
         assert bool(conflict[s]) == bool(r.conflict)
         if not r.conflict:
             assert trail[s] == r.trail_size
+
+
+def test_gpu_mt19937_multi_segment_batch(bivium, golden, oracle_mod, cuda_lib):
+    """A long single-point stream is cut into jump-ahead segments; the sample values must
+    still be the sequential mt19937 stream (1-worker order, mpi_predicter.cpp:3236-3242)."""
+    from pdsat_b200 import api
+    nv, _, offs, lits = bivium
+    db = api.ClauseDb(nv, offs, lits, device=0)
+    db.set_fixed_assumptions(list(golden["stream_lits"]))
+    sv = list(range(148, 178))
+    n, first = 300_000, 12_345
+    b = api.Batch(db, [api.Point(sv, n, api.MODE_MT19937, seed=2, first_sample=first),
+                       api.Point(sv[:7], 5000, api.MODE_MT19937, seed=3)], api.OUT_ASSIGN)
+    b.run()
+    for lo in (0, 63, 150_001, n - 40):
+        asg = b.assign(0, lo, 40)
+        A = oracle_mod.sample_assumptions(2, sv, first + lo, 40)
+        for s in range(40):
+            for j, v in enumerate(sv):
+                assert asg[s][v - 1] == (A[s][j] & 1), (lo, s, j)
+    # reseed to another window of the same stream without reallocating
+    b.reseed(0, 5, 777)
+    b.run()
+    asg = b.assign(0, n - 10, 10)
+    A = oracle_mod.sample_assumptions(5, sv, 777 + n - 10, 10)
+    for s in range(10):
+        for j, v in enumerate(sv):
+            assert asg[s][v - 1] == (A[s][j] & 1)
