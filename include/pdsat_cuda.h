@@ -81,7 +81,8 @@ typedef struct {
     uint64_t sum_trail;    /* over conflict-free samples                               */
     uint64_t sumsq_trail;  /* over conflict-free samples                               */
     uint64_t n_implied_any;/* conflict-free samples where BCP implied >= 1 literal     */
-    uint64_t reserved[2];
+    uint64_t queue_pops;   /* diagnostics: occurrence lists scanned (per 64-sample group) */
+    uint64_t implied_lits; /* diagnostics: distinct implied literals (per 64-sample group)*/
 } pdsat_cost;
 
 typedef struct {

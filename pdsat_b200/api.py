@@ -45,7 +45,8 @@ class CPoint(C.Structure):
 
 class CCost(C.Structure):
     _fields_ = [("n", C.c_uint64), ("n_conflict", C.c_uint64), ("n_full", C.c_uint64), ("sum_trail", C.c_uint64),
-                ("sumsq_trail", C.c_uint64), ("n_implied_any", C.c_uint64), ("reserved", C.c_uint64 * 2)]
+                ("sumsq_trail", C.c_uint64), ("n_implied_any", C.c_uint64), ("queue_pops", C.c_uint64),
+                ("implied_lits", C.c_uint64)]
 
 
 class CDbInfo(C.Structure):
@@ -129,6 +130,8 @@ class Cost:
     sum_trail: int
     sumsq_trail: int
     n_implied_any: int
+    queue_pops: int = 0
+    implied_lits: int = 0
 
 
 def _cpoints(points: Sequence[Point]):
@@ -155,7 +158,7 @@ def _cpoints(points: Sequence[Point]):
 
 def _costs(arr, n) -> List[Cost]:
     return [Cost(arr[i].n, arr[i].n_conflict, arr[i].n_full, arr[i].sum_trail, arr[i].sumsq_trail,
-                 arr[i].n_implied_any) for i in range(n)]
+                 arr[i].n_implied_any, arr[i].queue_pops, arr[i].implied_lits) for i in range(n)]
 
 
 class ClauseDb:

@@ -23,7 +23,7 @@ namespace pdsat {
 
 enum : uint8_t { LB_TRUE = 0, LB_FALSE = 1, LB_UNDEF = 2 };
 
-static constexpr uint16_t REC_PAD = 0xFFFF;   // unused literal slot
+// unused literal slots hold the code of the pad plane (= 2*n_live, "always false")
 static constexpr uint16_t REC_CONT = 0xFFFE;  // slot 7: clause continues in the next record
 static constexpr int REC_SLOTS = 8;           // uint16 slots per 16-byte record
 
@@ -52,6 +52,7 @@ struct HostDb {
                                           // FALSE plane (compact literal ^ 1)
     std::vector<uint32_t> occ_off;        // 2*n_live + 1
     std::vector<uint32_t> occ;            // record index of each clause containing the literal
+    std::vector<uint16_t> rec_len;        // clause length, indexed by its first record
     int64_t n_rec = 0;
     int64_t n_clauses_live = 0;
     int64_t n_lits_live = 0;
@@ -174,6 +175,7 @@ struct HostDb {
         }
         n_live = (int32_t)var_of_live.size();
         rec.clear();
+        rec_len.clear();
         occ_off.assign((size_t)2 * n_live + 1, 0);
         occ.clear();
         n_rec = n_clauses_live = n_lits_live = 0;
@@ -202,7 +204,7 @@ struct HostDb {
             while (true) {
                 size_t remaining = len - pos;
                 uint16_t slots[REC_SLOTS];
-                for (int s = 0; s < REC_SLOTS; s++) slots[s] = REC_PAD;
+                for (int s = 0; s < REC_SLOTS; s++) slots[s] = (uint16_t)(2 * n_live);
                 if (remaining <= REC_SLOTS) {
                     for (size_t s = 0; s < remaining; s++) slots[s] = (uint16_t)(cl[pos + s] ^ 1);
                     pos = len;
@@ -212,6 +214,7 @@ struct HostDb {
                     pos += REC_SLOTS - 1;
                 }
                 rec.insert(rec.end(), slots, slots + REC_SLOTS);
+                rec_len.push_back((uint16_t)(n_rec == (int64_t)first_rec ? len : 0));
                 n_rec++;
                 if (pos == len) break;
             }

@@ -42,6 +42,8 @@ struct PointDev {
     uint32_t var_off;      // offset into the set-code table
     uint32_t mode;
     uint32_t n_assumed_live;  // set variables that are not fixed at level 0
+    uint32_t cand_off;        // first-wave candidate clauses of this point
+    uint32_t cand_cnt;
 };
 
 static constexpr uint32_t SETCODE_FIXED = 0x80000000u;  // set var already assigned at level 0; bit0 = its lbool
@@ -52,6 +54,7 @@ struct BatchDev {
     uint64_t n_groups;
     uint64_t n_words;
     const uint32_t* setcode;
+    const uint32_t* cand;       // candidate clause (first-record) ids, all points
     uint64_t* words;
     const uint32_t* stream;
     unsigned long long* cost;   // n_points * 8
@@ -137,8 +140,11 @@ struct MtJumpTask {
     uint32_t src, dst, poly, pad;
 };
 
-static constexpr int MT_JUMP_THREADS = 640;
-static constexpr int MT_JUMP_ROUNDS = 33;  // 33 * 624 = 20592 >= 19937 + 623 words
+static constexpr int MT_JUMP_SLICES = 6;      // the polynomial's 624 words are cut into 6 x 104
+static constexpr int MT_JUMP_SLICE_WORDS = 104;
+static constexpr int MT_JUMP_V = 8;           // output words per thread (register window)
+static constexpr int MT_JUMP_THREADS = MT_JUMP_SLICES * 96;  // 78 of every 96 threads carry outputs
+static constexpr int MT_JUMP_ROUNDS = 34;     // 34 * 624 = 21216 >= 19968 + 8 + 623 words
 static constexpr int MT_JUMP_SMEM = (MT_JUMP_ROUNDS * 624 + 624) * 4;
 
 __global__ void __launch_bounds__(MT_JUMP_THREADS) mt19937_jump_kernel(const uint32_t* __restrict__ polys,
@@ -151,9 +157,9 @@ __global__ void __launch_bounds__(MT_JUMP_THREADS) mt19937_jump_kernel(const uin
     const MtJumpTask t = tasks[blockIdx.x];
     const uint32_t* src = states + (size_t)t.src * 624;
     const uint32_t* gp = polys + (size_t)t.poly * 624;
-    if (tid < 624) {
-        x[tid] = src[tid];
-        g[tid] = gp[tid];
+    for (int i = tid; i < 624; i += MT_JUMP_THREADS) {
+        x[i] = src[i];
+        g[i] = gp[i];
     }
     __syncthreads();
     // run the recurrence forward: x[n+624] = x[n+397] ^ twist(x[n], x[n+1])
@@ -171,18 +177,42 @@ __global__ void __launch_bounds__(MT_JUMP_THREADS) mt19937_jump_kernel(const uin
             __syncthreads();
         }
     }
-    if (tid < 624) {
-        uint32_t acc = 0;
-        for (int c = 0; c < 624; c++) {
-            uint32_t gw = g[c];
-            const uint32_t* xb = x + c * 32 + tid;
-            while (gw) {
-                const int b = __ffs(gw) - 1;
-                gw &= gw - 1;
-                acc ^= xb[b];
+    // correlation: thread (slice q, tp) accumulates output words 8*tp .. 8*tp+7 over the
+    // polynomial bits of slice q, sliding an 8-word register window along the sequence
+    const int q = tid / 96, tp = tid % 96;
+    uint32_t acc[MT_JUMP_V];
+#pragma unroll
+    for (int v = 0; v < MT_JUMP_V; v++) acc[v] = 0;
+    if (tp < 78) {
+        const int w0 = tp * MT_JUMP_V;
+        const int gw0 = q * MT_JUMP_SLICE_WORDS;
+        const uint32_t* xs = x + w0 + gw0 * 32;
+        uint32_t r[MT_JUMP_V];
+#pragma unroll
+        for (int v = 0; v < MT_JUMP_V; v++) r[v] = xs[v];
+        for (int gi = 0; gi < MT_JUMP_SLICE_WORDS; gi++) {
+            const uint32_t gw = g[gw0 + gi];
+            const uint32_t* xw = xs + gi * 32 + MT_JUMP_V;
+#pragma unroll
+            for (int b = 0; b < 32; b++) {
+                const uint32_t m = (uint32_t)((int32_t)(gw << (31 - b)) >> 31);
+#pragma unroll
+                for (int v = 0; v < MT_JUMP_V; v++) acc[v] ^= r[(b + v) % MT_JUMP_V] & m;
+                r[b % MT_JUMP_V] = xw[b];
             }
         }
-        states[(size_t)t.dst * 624 + tid] = acc;
+    }
+    __syncthreads();  // everyone is done reading x: reuse its head for the partial sums
+    if (tp < 78) {
+#pragma unroll
+        for (int v = 0; v < MT_JUMP_V; v++) x[q * 624 + tp * MT_JUMP_V + v] = acc[v];
+    }
+    __syncthreads();
+    for (int w = tid; w < 624; w += MT_JUMP_THREADS) {
+        uint32_t o = 0;
+#pragma unroll
+        for (int s = 0; s < MT_JUMP_SLICES; s++) o ^= x[s * 624 + w];
+        states[(size_t)t.dst * 624 + w] = o;
     }
 }
 
@@ -255,81 +285,120 @@ __global__ void __launch_bounds__(256) mt19937_bits_kernel(const uint32_t* __res
 }
 
 // ------------------------------------------------------------------ BCP
+// Per-warp working set in shared memory (one warp owns one group of 64 samples):
+//   S[l]      64-bit plane per literal: samples in which literal l is TRUE
+//   queue     ring of implied literals whose occurrence lists still have to be visited
+//   touched   log of the literals implied in this group (undo list: only these planes and
+//             the assumption planes are cleared before the next group)
+//   inq       bitset "literal is in the queue"
 struct WarpCtx {
-    uint64_t* S;        // [n_lit + 2] one plane per literal: samples where it is TRUE
-    uint16_t* queue;    // ring of literals whose occurrence lists must be visited
-    uint32_t* inq;      // bitset: literal currently queued
+    uint64_t* S;
+    uint16_t* queue;
+    uint16_t* touched;
+    uint32_t* inq;
     uint64_t* dead;     // samples in conflict
     uint32_t* qtail;
-    uint32_t* implied;  // set when BCP implied anything in this group
+    uint32_t* ntouched;
     uint32_t qmask;
 };
 
 __device__ __forceinline__ void push_lit(const WarpCtx& c, uint32_t l) {
-    uint32_t bit = 1u << (l & 31);
-    uint32_t old = atomicOr(&c.inq[l >> 5], bit);
+    const uint32_t bit = 1u << (l & 31);
+    const uint32_t old = atomicOr(&c.inq[l >> 5], bit);
     if (!(old & bit)) {
-        uint32_t pos = atomicAdd(c.qtail, 1u);
+        const uint32_t pos = atomicAdd(c.qtail, 1u);
         c.queue[pos & c.qmask] = (uint16_t)l;
     }
 }
 
-// Evaluate one clause on the 64 samples of the group.  Slots hold the code of each
-// literal's FALSE plane.  ge1 / ge2 = samples with >= 1 / >= 2 non-false literals.
-__device__ __forceinline__ void visit_clause(const uint4* __restrict__ rec, uint32_t ci, const WarpCtx& c,
-                                             uint64_t live) {
-    uint64_t ge1 = 0, ge2 = 0;
+__device__ __forceinline__ uint32_t rec_slot(const uint4& r, int j) {
+    const uint32_t w = j < 2 ? r.x : (j < 4 ? r.y : (j < 6 ? r.z : r.w));
+    return (j & 1) ? (w >> 16) : (w & 0xFFFFu);
+}
+
+// ge1 / ge2 = samples in which the clause has >= 1 / >= 2 non-false literals.  A record has
+// 8 slots, each the code of a literal's FALSE plane; unused slots point at the "always false"
+// pad plane (all ones), so the evaluation is branch-free; slot 7 == REC_CONT chains a clause
+// longer than 8 literals into the next record.
+__device__ __forceinline__ void eval_clause(const uint4* __restrict__ rec, uint32_t ci, const uint64_t* S,
+                                            uint64_t& ge1, uint64_t& ge2) {
+    ge1 = 0;
+    ge2 = 0;
     uint32_t cur = ci;
     bool more;
     do {
-        more = false;
         const uint4 r = __ldg(&rec[cur]);
-        const uint32_t w[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
-            uint32_t m = (w[j >> 1] >> ((j & 1) * 16)) & 0xFFFFu;
-            if (m >= 0xFFFEu) {
-                if (m == 0xFFFEu) {
-                    more = true;
-                    cur++;
-                }
-                break;
-            }
-            uint64_t nf = ~c.S[m];
+        for (int j = 0; j < 7; j++) {
+            const uint64_t nf = ~S[rec_slot(r, j)];
             ge2 |= ge1 & nf;
             ge1 |= nf;
         }
+        const uint32_t m7 = rec_slot(r, 7);
+        more = m7 == 0xFFFEu;
+        if (!more) {
+            const uint64_t nf = ~S[m7];
+            ge2 |= ge1 & nf;
+            ge1 |= nf;
+        }
+        cur++;
     } while (more);
+}
+
+// make literal (plane m^1) true in the samples `imp` where it is still undefined
+__device__ __forceinline__ void imply_lit(const WarpCtx& c, uint32_t m, uint64_t imp) {
+    imp &= ~c.S[m ^ 1];
+    if (imp) {
+        const uint64_t old = atomicOr((unsigned long long*)&c.S[m ^ 1], (unsigned long long)imp);
+        if (old == 0) c.touched[atomicAdd(c.ntouched, 1u)] = (uint16_t)(m ^ 1);
+        if (imp & ~old) push_lit(c, m ^ 1);
+    }
+}
+
+// rare path: in the samples of `unit` the clause has exactly one non-false literal; make it
+// true where it is still undefined (Solver.cc:641-648 uncheckedEnqueue(first, cr))
+__device__ __forceinline__ void imply_from_clause(const uint4* __restrict__ rec, uint32_t ci, const WarpCtx& c,
+                                                  uint64_t unit) {
+    uint32_t cur = ci;
+    bool more;
+    do {
+        const uint4 r = __ldg(&rec[cur]);
+#pragma unroll
+        for (int j = 0; j < 7; j++) {
+            const uint32_t m = rec_slot(r, j);
+            const uint64_t imp = unit & ~c.S[m];
+            if (imp) imply_lit(c, m, imp);
+        }
+        const uint32_t m7 = rec_slot(r, 7);
+        more = m7 == 0xFFFEu;
+        if (!more) {
+            const uint64_t imp = unit & ~c.S[m7];
+            if (imp) imply_lit(c, m7, imp);
+        }
+        cur++;
+    } while (more);
+}
+
+__device__ __forceinline__ void settle_clause(const uint4* __restrict__ rec, uint32_t ci, const WarpCtx& c,
+                                              uint64_t live, uint64_t ge1, uint64_t ge2) {
     const uint64_t confl = ~ge1 & live;
     const uint64_t unit = ge1 & ~ge2 & live;
     if (confl) atomicOr((unsigned long long*)c.dead, (unsigned long long)confl);
-    if (unit) {
-        // rare path: find, per sample, the one non-false literal and make it true
-        cur = ci;
-        do {
-            more = false;
-            const uint4 r = __ldg(&rec[cur]);
-            const uint32_t w[4] = {r.x, r.y, r.z, r.w};
-#pragma unroll
-            for (int j = 0; j < 8; j++) {
-                uint32_t m = (w[j >> 1] >> ((j & 1) * 16)) & 0xFFFFu;
-                if (m >= 0xFFFEu) {
-                    if (m == 0xFFFEu) {
-                        more = true;
-                        cur++;
-                    }
-                    break;
-                }
-                uint64_t imp = unit & ~c.S[m] & ~c.S[m ^ 1];
-                if (imp) {
-                    uint64_t old = atomicOr((unsigned long long*)&c.S[m ^ 1], (unsigned long long)imp);
-                    if (imp & ~old) {
-                        push_lit(c, m ^ 1);
-                        *c.implied = 1;
-                    }
-                }
-            }
-        } while (more);
+    if (unit) imply_from_clause(rec, ci, c, unit);
+}
+
+// visit list[0..n): two clauses per lane per trip so that their loads overlap
+__device__ __forceinline__ void visit_list(const uint4* __restrict__ rec, const uint32_t* __restrict__ list,
+                                           uint32_t n, const WarpCtx& c, uint64_t live, int lane) {
+    for (uint32_t i = lane; i < n; i += 64) {
+        const uint32_t c0 = __ldg(&list[i]);
+        const bool two = i + 32 < n;
+        const uint32_t c1 = two ? __ldg(&list[i + 32]) : c0;
+        uint64_t a1, a2, b1, b2;
+        eval_clause(rec, c0, c.S, a1, a2);
+        eval_clause(rec, c1, c.S, b1, b2);
+        settle_clause(rec, c0, c, live, a1, a2);
+        if (two) settle_clause(rec, c1, c, live, b1, b2);
     }
 }
 
@@ -343,9 +412,10 @@ __device__ __forceinline__ uint64_t shfl_down64(uint64_t v, int d) {
 }
 
 static constexpr int MAX_COUNT_BITS = 13;
+static constexpr int MULTI_POP = 8;  // queued literals processed per propagation round
 
 struct WarpAcc {
-    uint64_t n, n_conflict, n_full, sum, sumsq, n_impl;
+    uint64_t n, n_conflict, n_full, sum, sumsq, n_impl, pops, touched;
     int point;
 };
 
@@ -358,12 +428,22 @@ __device__ __forceinline__ void flush_acc(WarpAcc& a, unsigned long long* cost, 
         atomicAdd(&c[3], (unsigned long long)a.sum);
         atomicAdd(&c[4], (unsigned long long)a.sumsq);
         if (a.n_impl) atomicAdd(&c[5], (unsigned long long)a.n_impl);
+        if (a.pops) atomicAdd(&c[6], (unsigned long long)a.pops);
+        if (a.touched) atomicAdd(&c[7], (unsigned long long)a.touched);
     }
-    a.n = a.n_conflict = a.n_full = a.sum = a.sumsq = a.n_impl = 0;
+    a.n = a.n_conflict = a.n_full = a.sum = a.sumsq = a.n_impl = a.pops = a.touched = 0;
 }
 
-// Persistent kernel: grid = #SMs x CTAs/SM, each warp strides over the groups.
-__global__ void __launch_bounds__(1024, 1)
+// Persistent kernel: grid = #SMs, each warp strides over the 64-sample groups.
+//
+// Per group:  (1) write the assumption planes;  (2) FIRST WAVE: visit the point's candidate
+// clauses - the only clauses that can be unit or falsified when just the set variables are
+// assigned are those with at most one literal outside the set (computed once per point on
+// the host; MiniSat gets the same effect lazily from its two watched literals);
+// (3) drain the queue of implied literals, visiting every clause that contains the
+// complement of a literal that became true (Solver.cc:611-655);  (4) per-sample results and
+// integer cost accumulation;  (5) undo: clear only the planes that were written.
+__global__ void __launch_bounds__(512, 1)
 bcp_kernel(DbDev db, BatchDev b, int warp_bytes, int qcap) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int lane = threadIdx.x & 31;
@@ -374,15 +454,21 @@ bcp_kernel(DbDev db, BatchDev b, int warp_bytes, int qcap) {
     c.S = (uint64_t*)base;
     const int n_planes = db.n_lit + 2;
     c.queue = (uint16_t*)(c.S + n_planes);
-    c.inq = (uint32_t*)(c.queue + qcap);
+    c.touched = c.queue + qcap;                 // qcap (a power of two) ring slots
+    c.inq = (uint32_t*)(c.touched + ((db.n_lit + 2 + 3) & ~3));
     const int inq_words = (db.n_lit + 31) >> 5;
     c.dead = (uint64_t*)(c.inq + ((inq_words + 1) & ~1));
     c.qtail = (uint32_t*)(c.dead + 1);
-    c.implied = c.qtail + 1;
+    c.ntouched = c.qtail + 1;
     c.qmask = (uint32_t)qcap - 1;
 
+    // the planes start clean and every group cleans up after itself
+    for (int i = lane; i < n_planes; i += 32) c.S[i] = i == db.n_lit ? ~0ull : 0ull;  // plane n_lit = pad
+    for (int i = lane; i < inq_words; i += 32) c.inq[i] = 0;
+    __syncwarp();
+
     WarpAcc acc;
-    acc.n = acc.n_conflict = acc.n_full = acc.sum = acc.sumsq = acc.n_impl = 0;
+    acc.n = acc.n_conflict = acc.n_full = acc.sum = acc.sumsq = acc.n_impl = acc.pops = acc.touched = 0;
     acc.point = -1;
 
     const uint64_t stride = (uint64_t)gridDim.x * wpc;
@@ -398,21 +484,18 @@ bcp_kernel(DbDev db, BatchDev b, int warp_bytes, int qcap) {
         const uint64_t left = pt->n_samples - s0;
         const uint64_t valid = left >= 64 ? ~0ull : ((1ull << left) - 1);
         const uint32_t k = pt->k;
+        const uint32_t* code = b.setcode + pt->var_off;
 
-        // ---- reset the group's state
-        for (int i = lane; i < n_planes; i += 32) c.S[i] = 0;
-        for (int i = lane; i < inq_words; i += 32) c.inq[i] = 0;
         if (lane == 0) {
             *c.dead = db.unsat ? valid : 0;
             *c.qtail = 0;
-            *c.implied = 0;
+            *c.ntouched = 0;
         }
         __syncwarp();
 
-        // ---- assumptions (src_mpi/mpi_predicter.cpp:3236-3242: true bit => positive literal)
+        // ---- (1) assumptions (src_mpi/mpi_predicter.cpp:3236-3242: true bit => positive literal)
         if (!db.unsat) {
             const uint64_t* w = b.words + pt->word_off + gi * k;
-            const uint32_t* code = b.setcode + pt->var_off;
             for (uint32_t j = lane; j < k; j += 32) {
                 const uint32_t cd = code[j];
                 const uint64_t bits = w[j];
@@ -422,51 +505,96 @@ bcp_kernel(DbDev db, BatchDev b, int warp_bytes, int qcap) {
                     const uint64_t bad = ((cd & 1u) ? bits : ~bits) & valid;
                     if (bad) atomicOr((unsigned long long*)c.dead, (unsigned long long)bad);
                 } else {
-                    const uint64_t tp = bits & valid, tn = ~bits & valid;
-                    c.S[cd] = tp;
-                    c.S[cd ^ 1] = tn;
-                    if (tp) push_lit(c, cd);
-                    if (tn) push_lit(c, cd ^ 1);
+                    c.S[cd] = bits & valid;
+                    c.S[cd ^ 1] = ~bits & valid;
                 }
             }
-        }
-        __syncwarp();
+            __syncwarp();
 
-        // ---- propagate to the fixpoint
-        uint32_t qh = 0;
-        while (true) {
-            const uint32_t qt = *(volatile uint32_t*)c.qtail;
-            const uint64_t deadv = *(volatile uint64_t*)c.dead;
-            if (qh == qt || (deadv & valid) == valid) break;
-            const uint32_t l = c.queue[qh & c.qmask];
-            qh++;
-            __syncwarp();
-            if (lane == 0) atomicAnd(&c.inq[l >> 5], ~(1u << (l & 31)));
-            __syncwarp();
-            const uint64_t live = valid & ~deadv;
-            const uint32_t nl = l ^ 1;  // this literal just became false somewhere
-            const uint32_t beg = __ldg(&db.occ_off[nl]), end = __ldg(&db.occ_off[nl + 1]);
-            for (uint32_t i = beg + lane; i < end; i += 32) visit_clause(db.rec, __ldg(&db.occ[i]), c, live);
+            // ---- (2) first wave over the point's candidate clauses
+            if (pt->cand_cnt) {
+                const uint64_t live = valid & ~*(volatile uint64_t*)c.dead;
+                visit_list(db.rec, b.cand + pt->cand_off, pt->cand_cnt, c, live, lane);
+                __syncwarp();
+            }
+
+            // ---- (3) propagate the implied literals to the fixpoint.  Up to MULTI_POP
+            // queued literals are taken per round; their occurrence lists are visited as one
+            // concatenated list so that the dependent loads of several literals overlap.
+            uint32_t qh = 0;
+            while (true) {
+                const uint32_t qt = *(volatile uint32_t*)c.qtail;
+                const uint64_t deadv = *(volatile uint64_t*)c.dead;
+                if (qh == qt || (deadv & valid) == valid) break;
+                const uint32_t np = min(qt - qh, (uint32_t)MULTI_POP);
+                uint32_t myl = 0, mybeg = 0, mylen = 0;
+                if (lane < (int)np) myl = c.queue[(qh + lane) & c.qmask];
+                qh += np;
+                __syncwarp();
+                if (lane < (int)np) {
+                    atomicAnd(&c.inq[myl >> 5], ~(1u << (myl & 31)));
+                    const uint32_t nl = myl ^ 1;  // this literal just became false somewhere
+                    mybeg = __ldg(&db.occ_off[nl]);
+                    mylen = __ldg(&db.occ_off[nl + 1]) - mybeg;
+                }
+                uint32_t cum = mylen;  // inclusive scan over the first MULTI_POP lanes
+#pragma unroll
+                for (int d = 1; d < MULTI_POP; d <<= 1) {
+                    const uint32_t up = __shfl_up_sync(0xffffffffu, cum, d);
+                    if (lane >= d) cum += up;
+                }
+                const uint32_t total = __shfl_sync(0xffffffffu, cum, MULTI_POP - 1);
+                uint32_t bound[MULTI_POP], base[MULTI_POP];
+#pragma unroll
+                for (int q = 0; q < MULTI_POP; q++) {
+                    bound[q] = __shfl_sync(0xffffffffu, cum, q);
+                    base[q] = __shfl_sync(0xffffffffu, mybeg - (cum - mylen), q);  // occ index = base + i
+                }
+                __syncwarp();
+                const uint64_t live = valid & ~deadv;
+                for (uint32_t i = lane; i < total; i += 64) {
+                    const bool two = i + 32 < total;
+                    const uint32_t i1 = two ? i + 32 : i;
+                    uint32_t o0 = base[0], o1 = base[0];
+#pragma unroll
+                    for (int q = 1; q < MULTI_POP; q++) {
+                        if (i >= bound[q - 1]) o0 = base[q];
+                        if (i1 >= bound[q - 1]) o1 = base[q];
+                    }
+                    const uint32_t c0 = __ldg(&db.occ[o0 + i]);
+                    const uint32_t c1 = __ldg(&db.occ[o1 + i1]);
+                    uint64_t a1, a2, b1, b2;
+                    eval_clause(db.rec, c0, c.S, a1, a2);
+                    eval_clause(db.rec, c1, c.S, b1, b2);
+                    settle_clause(db.rec, c0, c, live, a1, a2);
+                    if (two) settle_clause(db.rec, c1, c, live, b1, b2);
+                }
+                __syncwarp();
+            }
+            acc.pops += qh;
             __syncwarp();
         }
-        __syncwarp();
 
-        // ---- per-sample results
+        // ---- (4) per-sample results
         const uint64_t dead = *c.dead & valid;
         const uint64_t okm = valid & ~dead;
-        const bool any_impl = *c.implied != 0;
+        const uint32_t n_touched = *c.ntouched;
+        acc.touched += n_touched;
         uint32_t cnt0, cnt1;  // assigned live variables of samples lane, lane+32
-        if (!any_impl) {
+        if (n_touched == 0) {
             cnt0 = cnt1 = pt->n_assumed_live;
         } else {
+            // bit-sliced population count over the implied planes: per sample, how many
+            // literals of the undo list are set (each implied variable has one polarity per
+            // conflict-free sample)
             uint64_t cb[MAX_COUNT_BITS];
 #pragma unroll
             for (int q = 0; q < MAX_COUNT_BITS; q++) cb[q] = 0;
-            for (int v = lane; v < db.n_live; v += 32) {
-                uint64_t carry = c.S[2 * v] | c.S[2 * v + 1];
+            for (uint32_t i = lane; i < n_touched; i += 32) {
+                uint64_t carry = c.S[c.touched[i]];
 #pragma unroll
                 for (int q = 0; q < MAX_COUNT_BITS; q++) {
-                    uint64_t t = cb[q] & carry;
+                    const uint64_t t = cb[q] & carry;
                     cb[q] ^= carry;
                     carry = t;
                 }
@@ -476,9 +604,9 @@ bcp_kernel(DbDev db, BatchDev b, int warp_bytes, int qcap) {
                 uint64_t carry = 0;
 #pragma unroll
                 for (int q = 0; q < MAX_COUNT_BITS; q++) {
-                    uint64_t o = shfl_down64(cb[q], off);
-                    uint64_t x = cb[q] ^ o;
-                    uint64_t s = x ^ carry;
+                    const uint64_t o = shfl_down64(cb[q], off);
+                    const uint64_t x = cb[q] ^ o;
+                    const uint64_t s = x ^ carry;
                     carry = (cb[q] & o) | (carry & x);
                     cb[q] = s;
                 }
@@ -486,28 +614,33 @@ bcp_kernel(DbDev db, BatchDev b, int warp_bytes, int qcap) {
             cnt0 = cnt1 = 0;
 #pragma unroll
             for (int q = 0; q < MAX_COUNT_BITS; q++) {
-                uint64_t t = shfl64(cb[q], 0);
+                const uint64_t t = shfl64(cb[q], 0);
                 cnt0 |= (uint32_t)((t >> lane) & 1ull) << q;
                 cnt1 |= (uint32_t)((t >> (lane + 32)) & 1ull) << q;
             }
+            cnt0 += pt->n_assumed_live;
+            cnt1 += pt->n_assumed_live;
         }
         const bool ok0 = (okm >> lane) & 1ull, ok1 = (okm >> (lane + 32)) & 1ull;
         const uint32_t full_lo = __ballot_sync(0xffffffffu, ok0 && cnt0 == (uint32_t)db.n_live);
         const uint32_t full_hi = __ballot_sync(0xffffffffu, ok1 && cnt1 == (uint32_t)db.n_live);
         const uint64_t fullm = ((uint64_t)full_hi << 32) | full_lo;
         const uint32_t t0 = db.n_base_assigned + cnt0, t1 = db.n_base_assigned + cnt1;
-        uint32_t lsum = (ok0 ? t0 : 0) + (ok1 ? t1 : 0);
-        uint32_t lsq = (ok0 ? t0 * t0 : 0) + (ok1 ? t1 * t1 : 0);
-        uint32_t limp = (ok0 && cnt0 > pt->n_assumed_live ? 1 : 0) + (ok1 && cnt1 > pt->n_assumed_live ? 1 : 0);
-        lsum = __reduce_add_sync(0xffffffffu, lsum);
-        lsq = __reduce_add_sync(0xffffffffu, lsq);
-        limp = __reduce_add_sync(0xffffffffu, limp);
+        if (n_touched == 0) {
+            const uint64_t nok = __popcll(okm);
+            acc.sum += nok * t0;
+            acc.sumsq += nok * (uint64_t)t0 * t0;
+        } else {
+            uint32_t lsum = (ok0 ? t0 : 0) + (ok1 ? t1 : 0);
+            uint32_t lsq = (ok0 ? t0 * t0 : 0) + (ok1 ? t1 * t1 : 0);
+            uint32_t limp = (ok0 && cnt0 > pt->n_assumed_live ? 1 : 0) + (ok1 && cnt1 > pt->n_assumed_live ? 1 : 0);
+            acc.sum += __reduce_add_sync(0xffffffffu, lsum);
+            acc.sumsq += __reduce_add_sync(0xffffffffu, lsq);
+            acc.n_impl += __reduce_add_sync(0xffffffffu, limp);
+        }
         acc.n += __popcll(valid);
         acc.n_conflict += __popcll(dead);
         acc.n_full += __popcll(fullm);
-        acc.sum += lsum;
-        acc.sumsq += lsq;
-        acc.n_impl += limp;
 
         if (b.conflict_bits && lane == 0) {
             b.conflict_bits[g] = dead;
@@ -542,6 +675,23 @@ bcp_kernel(DbDev db, BatchDev b, int warp_bytes, int qcap) {
                         b.model_sample[idx] = s0 + s;
                     }
                 }
+            }
+        }
+        __syncwarp();
+
+        // ---- (5) undo: clear the assumption planes, the implied planes and the queue flags
+        if (!db.unsat) {
+            for (uint32_t j = lane; j < k; j += 32) {
+                const uint32_t cd = code[j];
+                if (!(cd & SETCODE_FIXED)) {
+                    c.S[cd] = 0;
+                    c.S[cd ^ 1] = 0;
+                }
+            }
+            for (uint32_t i = lane; i < n_touched; i += 32) {
+                const uint32_t l = c.touched[i];
+                c.S[l] = 0;
+                atomicAnd(&c.inq[l >> 5], ~(1u << (l & 31)));
             }
         }
         __syncwarp();

@@ -54,6 +54,8 @@ struct HostPoint {
     uint64_t n_groups = 0, group_start = 0, word_off = 0, stream_off = 0, stream_skip = 0, stream_words = 0;
     uint64_t mt_first_round = 0, mt_rounds = 0;
     uint32_t n_assumed_live = 0;
+    std::vector<uint32_t> cand;  // first-wave candidate clauses (first-record ids)
+    uint32_t cand_off = 0;
     // mt19937 stream segments of 2^mt_m rounds each
     uint32_t mt_index = 0;      // index among the batch's mt19937 points (= state slot of segment 0)
     uint32_t n_segs = 0;
@@ -71,6 +73,7 @@ struct pdsat_batch {
     // device
     PointDev* d_points = nullptr;
     uint32_t* d_setcode = nullptr;
+    uint32_t* d_cand = nullptr;
     uint64_t* d_words = nullptr;
     uint32_t* d_stream = nullptr;
     unsigned long long* d_cost = nullptr;
@@ -143,10 +146,10 @@ static int sync_device_db(pdsat_db* db) {
     if (count_bits_for(h.n_live) > MAX_COUNT_BITS) return fail(PDSAT_ERR_LIMIT, "too many live variables for the counters");
     int n_lit = 2 * h.n_live;
     int n_planes = n_lit + 2;
-    int qcap = 4;
+    int qcap = 4;  // queue ring (power of two >= one slot per literal)
     while (qcap < n_lit + 2) qcap <<= 1;
     int inq_words = (n_lit + 31) / 32;
-    int warp_bytes = n_planes * 8 + qcap * 2 + ((inq_words + 1) & ~1) * 4 + 16;
+    int warp_bytes = n_planes * 8 + qcap * 2 + ((n_lit + 2 + 3) & ~3) * 2 + ((inq_words + 1) & ~1) * 4 + 16;
     warp_bytes = (warp_bytes + 15) & ~15;
     db->qcap = qcap;
     db->warp_bytes = warp_bytes;
@@ -159,7 +162,7 @@ static int sync_device_db(pdsat_db* db) {
     const int max_smem = 227 * 1024;
     int wpc = max_smem / warp_bytes;
     if (wpc < 1) return fail(PDSAT_ERR_LIMIT, "assignment state of one sample group exceeds shared memory");
-    if (wpc > 32) wpc = 32;
+    if (wpc > 16) wpc = 16;  // __launch_bounds__(512)
     db->warps_per_cta = wpc;
     db->smem_bytes = wpc * warp_bytes;
     db->grid = db->sm_count;
@@ -320,8 +323,10 @@ int pdsat_batch_create(pdsat_db* db, int32_t n_points, const pdsat_point* points
     if (b->model_words == 0) b->model_words = 1;
     b->pts.resize(n_points);
     uint64_t groups = 0, words = 0, stream_words = 0;
-    size_t n_codes = 0;
+    size_t n_codes = 0, n_cand = 0;
     std::vector<uint8_t> seen((size_t)h.n_vars);
+    std::vector<uint16_t> in_set_count((size_t)h.n_rec + 1, 0);
+    std::vector<uint32_t> touched_rec;
     for (int p = 0; p < n_points; p++) {
         const pdsat_point& in = points[p];
         HostPoint& hp = b->pts[p];
@@ -349,6 +354,28 @@ int pdsat_batch_create(pdsat_db* db, int32_t n_points, const pdsat_point* points
                 hp.n_assumed_live++;
             }
         }
+        // first-wave candidates: clauses with at most one literal outside the set
+        if (h.base_ok) {
+            touched_rec.clear();
+            for (int j = 0; j < in.k; j++) {
+                const int32_t lv = h.live_of_var[in.set_vars[j] - 1];
+                if (lv < 0) continue;
+                for (int sgn = 0; sgn < 2; sgn++) {
+                    const uint32_t l = (uint32_t)(2 * lv + sgn);
+                    for (uint32_t o = h.occ_off[l]; o < h.occ_off[l + 1]; o++) {
+                        const uint32_t r = h.occ[o];
+                        if (in_set_count[r]++ == 0) touched_rec.push_back(r);
+                    }
+                }
+            }
+            for (uint32_t r : touched_rec) {
+                if ((int)in_set_count[r] + 1 >= (int)h.rec_len[r]) hp.cand.push_back(r);
+                in_set_count[r] = 0;
+            }
+            std::sort(hp.cand.begin(), hp.cand.end());
+        }
+        hp.cand_off = (uint32_t)n_cand;
+        n_cand += hp.cand.size();
         hp.mode = in.mode;
         hp.seed = in.seed;
         hp.first_sample = in.first_sample;
@@ -412,6 +439,7 @@ int pdsat_batch_create(pdsat_db* db, int32_t n_points, const pdsat_point* points
     CUB(cudaMalloc(&b->d_points, sizeof(PointDev) * n_points));
     CUB(cudaMallocHost(&b->h_points, sizeof(PointDev) * n_points));
     CUB(cudaMalloc(&b->d_setcode, sizeof(uint32_t) * n_codes));
+    CUB(cudaMalloc(&b->d_cand, sizeof(uint32_t) * (n_cand ? n_cand : 1)));
     CUB(cudaMalloc(&b->d_words, sizeof(uint64_t) * words));
     CUB(cudaMalloc(&b->d_stream, sizeof(uint32_t) * (stream_words ? stream_words : 1)));
     CUB(cudaMalloc(&b->d_cost, sizeof(unsigned long long) * PDSAT_COST_WORDS * n_points));
@@ -480,8 +508,13 @@ int pdsat_batch_create(pdsat_db* db, int32_t n_points, const pdsat_point* points
             pd.var_off = off;
             pd.mode = (uint32_t)hp.mode;
             pd.n_assumed_live = hp.n_assumed_live;
+            pd.cand_off = hp.cand_off;
+            pd.cand_cnt = (uint32_t)hp.cand.size();
             off += pd.k;
             codes.insert(codes.end(), hp.setcode.begin(), hp.setcode.end());
+            if (!hp.cand.empty())
+                CUB(cudaMemcpy(b->d_cand + hp.cand_off, hp.cand.data(), sizeof(uint32_t) * hp.cand.size(),
+                               cudaMemcpyHostToDevice));
         }
         CUB(cudaMemcpy(b->d_setcode, codes.data(), sizeof(uint32_t) * n_codes, cudaMemcpyHostToDevice));
         CUB(cudaMemcpy(b->d_points, b->h_points, sizeof(PointDev) * n_points, cudaMemcpyHostToDevice));
@@ -625,6 +658,7 @@ int pdsat_batch_propagate(pdsat_batch* b) {
     bd.n_groups = b->n_groups;
     bd.n_words = b->n_words;
     bd.setcode = b->d_setcode;
+    bd.cand = b->d_cand;
     bd.words = b->d_words;
     bd.stream = b->d_stream;
     bd.cost = cost;
@@ -783,6 +817,7 @@ void pdsat_batch_destroy(pdsat_batch* b) {
     }
     cudaFree(b->d_points);
     cudaFree(b->d_setcode);
+    cudaFree(b->d_cand);
     cudaFree(b->d_words);
     cudaFree(b->d_stream);
     cudaFree(b->d_cost);

@@ -279,3 +279,53 @@ def test_gpu_mt19937_multi_segment_batch(bivium, golden, oracle_mod, cuda_lib):
     for s in range(10):
         for j, v in enumerate(sv):
             assert asg[s][v - 1] == (A[s][j] & 1)
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+def test_gpu_random_cnfs(seed, oracle_mod, cuda_lib):
+    """Random CNFs with mixed clause lengths (binary ... 12 literals, i.e. chained records),
+    unit clauses at level 0, random sets: every enumerated assignment against the oracle.
+    Exercises the first-wave candidate analysis and the queue-driven propagation on
+    structures unlike Bivium."""
+    from pdsat_b200 import api, fixtures as fx
+    rng = np.random.default_rng(100 + seed)
+    nv = int(rng.integers(20, 60))
+    clauses = []
+    for _ in range(int(nv * rng.uniform(1.5, 3.5))):
+        ln = int(rng.choice([2, 2, 3, 3, 3, 4, 5, 9, 12]))
+        ln = min(ln, nv)
+        vs = rng.choice(np.arange(1, nv + 1), size=ln, replace=False)
+        clauses.append([int(v) * (1 if rng.integers(0, 2) else -1) for v in vs])
+    for _ in range(int(rng.integers(0, 3))):
+        clauses.append([int(rng.integers(1, nv + 1)) * (1 if rng.integers(0, 2) else -1)])
+    offs, lits = fx.to_csr(clauses)
+    P = oracle_mod.Oracle(nv, offs, lits, "port")
+    db = api.ClauseDb(nv, offs, lits, device=0)
+    if db.info().status != api.PDSAT_OK:
+        assert not P.ok()
+        return
+    pts, sets = [], []
+    for _ in range(4):
+        k = int(rng.integers(1, 11))
+        sv = sorted(int(v) for v in rng.choice(np.arange(1, nv + 1), size=k, replace=False))
+        sets.append(sv)
+        pts.append(api.Point(sv, 1 << k, api.MODE_ENUM))
+    b = api.Batch(db, pts, api.OUT_FLAGS | api.OUT_TRAIL | api.OUT_ASSIGN, max_models=4096)
+    costs = b.run()
+    total_full = 0
+    for p, sv in enumerate(sets):
+        conflict, full = b.flags(p)
+        trail = b.trail(p)
+        asg = b.assign(p)
+        for s in range(1 << len(sv)):
+            r, a = P.bcp(list(oracle_mod.enum_assumptions(sv, s)))
+            assert bool(conflict[s]) == bool(r.conflict), (p, s)
+            if not r.conflict:
+                assert trail[s] == r.trail_size and bool(full[s]) == bool(r.full), (p, s)
+                assert (asg[s] == a).all(), (p, s)
+                total_full += r.full
+    found, _, _, models = b.models()
+    assert found == total_full
+    for m in models:
+        for cl in clauses:
+            assert any((m[abs(l) - 1] == 1) == (l > 0) for l in cl)
