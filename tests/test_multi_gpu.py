@@ -1,0 +1,63 @@
+"""GPU, N = 2 ranks over NCCL (skipped on a 1-GPU box): sample sharding + one all-reduce must
+give exactly the single-GPU accumulators (integer sums are rank-count independent)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, sets, n, q):
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    import bench
+    from pdsat_b200 import api, predicter as pr
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    nv, cl, offs, lits, stream = bench.instance()
+    db = api.ClauseDb(nv, offs, lits, device=rank)
+    db.set_fixed_assumptions(stream)
+
+    def all_reduce(arr):
+        t = torch.from_numpy(arr).cuda()
+        dist.all_reduce(t)
+        return t.cpu().numpy()
+
+    P = pr.Predicter(db, cnf_in_set_count=n, rank=rank, world=world, all_reduce=all_reduce)
+    res = P.evaluate(sets)
+    if rank == 0:
+        q.put([[r.cost.n, r.cost.n_conflict, r.cost.n_full, r.cost.sum_trail, r.cost.sumsq_trail] for r in res])
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_gpu_matches_one_gpu(cuda_lib):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    import bench
+    from pdsat_b200 import api, predicter as pr
+    sets = [list(range(148, 178)), [177 - i for i in range(86)], [177 - i for i in range(87)], [3, 5, 9]]
+    n = 100_003
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, 29650, sets, n, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=300)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    nv, cl, offs, lits, stream = bench.instance()
+    db = api.ClauseDb(nv, offs, lits, device=0)
+    db.set_fixed_assumptions(stream)
+    one = pr.Predicter(db, cnf_in_set_count=n).evaluate(sets)
+    for g, r in zip(got, one):
+        assert g == [r.cost.n, r.cost.n_conflict, r.cost.n_full, r.cost.sum_trail, r.cost.sumsq_trail]
