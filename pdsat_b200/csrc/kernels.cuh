@@ -216,71 +216,91 @@ __global__ void __launch_bounds__(MT_JUMP_THREADS) mt19937_jump_kernel(const uin
     }
 }
 
-// One CTA (256 threads) per stream segment.  states[state_base + blockIdx.x] is the 624-word
-// generator state *before* the twist that produces the segment's first round.  Emits, per
-// draw, the bool_rand bit ((tempered >> 31) == 0), packed little-endian into 32-bit words.
-__global__ void __launch_bounds__(256) mt19937_bits_kernel(const uint32_t* __restrict__ states,
-                                                           const MtSegment* __restrict__ segs,
-                                                           uint32_t* __restrict__ out) {
-    __shared__ uint32_t st[624];
-    __shared__ uint32_t pairw[40];
-    const int tid = threadIdx.x;
-    const MtSegment seg = segs[blockIdx.x];
+// ---- warp-register mt19937: one WARP per stream segment, the 624-word state lives in 20
+// registers per lane (R[c] of lane l = mt[32c + l]); a round is 20 chunks of 32 words updated
+// in place, neighbours fetched with warp shuffles - no shared memory, no block barriers:
+//     mt[k] <- mt[(k+397) % 624] ^ twist(mt[k], mt[(k+1) % 624])
+// Per draw only the bool_rand bit is needed: bool_rand == !(tempered >> 31), and bit 31 of the
+// tempered word is parity(y & 0x89010000) of the raw word y (bits 31, 27, 24, 16 - follows
+// from the four tempering shifts/masks).  Bits are packed little-endian, 39 words per 2 rounds.
+struct MtWarp {
+    uint32_t R[20];
+    uint32_t carry;         // pending low half-word of an odd round
+    uint32_t keepA, keepB;  // lane i holds output word i (keepA) / 32+i (keepB) of the round pair
+    int lane;
+
+    template <int IDX>
+    __device__ __forceinline__ void emit(uint32_t word) {
+        if (IDX < 32) keepA = lane == IDX ? word : keepA;
+        else keepB = lane == IDX - 32 ? word : keepB;
+    }
+    template <int C, int ODD>
+    __device__ __forceinline__ void chunk() {
+        const uint32_t a = R[C];
+        uint32_t b, m;
+        if (C < 19) {
+            const uint32_t v = lane >= 1 ? R[C] : R[C + 1];
+            b = __shfl_sync(0xffffffffu, v, (lane + 1) & 31);
+        } else {  // k = 608..623: the last word pairs with the NEW mt[0]
+            const uint32_t v = lane == 0 ? R[0] : R[19];
+            b = __shfl_sync(0xffffffffu, v, (lane + 1) & 15);
+        }
+        if (C < 7) {  // k + 397 < 624: old words of chunks C+12, C+13
+            const uint32_t v = lane >= 13 ? R[C + 12] : R[(C + 13) % 20];
+            m = __shfl_sync(0xffffffffu, v, (lane + 13) & 31);
+        } else if (C == 7) {  // straddles the wrap: old mt[621..623], then new mt[0..28]
+            const uint32_t m_old = __shfl_sync(0xffffffffu, R[19], (lane + 13) & 31);
+            const uint32_t m_new = __shfl_sync(0xffffffffu, R[0], (lane + 29) & 31);
+            m = lane < 3 ? m_old : m_new;
+        } else {  // k - 227: new words of chunks C-8, C-7
+            const uint32_t v = lane >= 29 ? R[(C + 12) % 20] : R[(C + 13) % 20];
+            m = __shfl_sync(0xffffffffu, v, (lane + 29) & 31);
+        }
+        const uint32_t y = (a & 0x80000000u) | (b & 0x7fffffffu);
+        const uint32_t nv = m ^ (y >> 1) ^ ((0u - (b & 1u)) & 0x9908b0dfu);
+        R[C] = nv;
+        const uint32_t bit = (__popc(nv & 0x89010000u) & 1u) ^ 1u;
+        uint32_t w = __ballot_sync(0xffffffffu, bit);
+        if (C == 19) w &= 0xffffu;
+        if (!ODD) {
+            if (C < 19) emit<C>(w);
+            else carry = w;
+        } else {
+            emit<19 + C>(carry | (w << 16));
+            carry = w >> 16;
+        }
+    }
+    template <int ODD>
+    __device__ __forceinline__ void round() {
+        chunk<0, ODD>(); chunk<1, ODD>(); chunk<2, ODD>(); chunk<3, ODD>(); chunk<4, ODD>();
+        chunk<5, ODD>(); chunk<6, ODD>(); chunk<7, ODD>(); chunk<8, ODD>(); chunk<9, ODD>();
+        chunk<10, ODD>(); chunk<11, ODD>(); chunk<12, ODD>(); chunk<13, ODD>(); chunk<14, ODD>();
+        chunk<15, ODD>(); chunk<16, ODD>(); chunk<17, ODD>(); chunk<18, ODD>(); chunk<19, ODD>();
+    }
+};
+
+static constexpr int MT_BITS_WARPS = 4;  // warps (= segments) per CTA
+
+__global__ void __launch_bounds__(MT_BITS_WARPS * 32) mt19937_bits_kernel(const uint32_t* __restrict__ states,
+                                                                          const MtSegment* __restrict__ segs,
+                                                                          int n_segs, uint32_t* __restrict__ out) {
+    const int seg_i = blockIdx.x * MT_BITS_WARPS + (threadIdx.x >> 5);
+    if (seg_i >= n_segs) return;
+    const MtSegment seg = segs[seg_i];
+    MtWarp g;
+    g.lane = threadIdx.x & 31;
     const uint32_t* s0 = states + (size_t)seg.state_idx * 624;
-    for (int i = tid; i < 624; i += 256) st[i] = s0[i];
-    if (tid < 40) pairw[tid] = 0;
-    __syncthreads();
-    uint32_t* dst = out + seg.out_off;
-    for (uint64_t r = 0; r < seg.n_rounds; r++) {
-        // twist: x[i] <- x[i+397] ^ twist(x[i], x[i+1]) in three dependency-free phases
-        const int base[3] = {0, 227, 454};
-        const int cnt[3] = {227, 227, 170};
 #pragma unroll
-        for (int ph = 0; ph < 3; ph++) {
-            uint32_t nv = 0;
-            int i = base[ph] + tid;
-            if (tid < cnt[ph]) {
-                uint32_t y = (st[i] & 0x80000000u) | (st[(i + 1) % 624] & 0x7fffffffu);
-                nv = st[(i + 397) % 624] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
-            }
-            __syncthreads();
-            if (tid < cnt[ph]) st[i] = nv;
-            __syncthreads();
-        }
-        // temper + bool_rand bit, 32 draws per ballot
-        const int odd = (int)(r & 1);
-#pragma unroll
-        for (int m = 0; m < 3; m++) {
-            int t = tid + 256 * m;
-            uint32_t bit = 0;
-            if (t < 624) {
-                uint32_t y = st[t];
-                y ^= y >> 11;
-                y ^= (y << 7) & 0x9d2c5680u;
-                y ^= (y << 15) & 0xefc60000u;
-                y ^= y >> 18;
-                bit = (y >> 31) == 0;
-            }
-            uint32_t word = __ballot_sync(0xffffffffu, bit);
-            if ((tid & 31) == 0 && t < 624) {
-                int c = t >> 5;  // chunk 0..19
-                if (!odd) {
-                    if (c < 19) pairw[c] = word;
-                    else atomicOr(&pairw[19], word & 0xffffu);
-                } else {
-                    atomicOr(&pairw[19 + c], word << 16);
-                    if (c < 19) atomicOr(&pairw[20 + c], word >> 16);
-                }
-            }
-        }
-        __syncthreads();
-        if (odd) {
-            if (tid < 39) {
-                dst[(r >> 1) * 39 + tid] = pairw[tid];
-                pairw[tid] = 0;
-            }
-            __syncthreads();
-        }
+    for (int c = 0; c < 20; c++) g.R[c] = (32 * c + g.lane < 624) ? s0[32 * c + g.lane] : 0u;
+    g.carry = 0;
+    g.keepA = g.keepB = 0;
+    uint32_t* dst = out + seg.out_off + g.lane;
+    for (uint64_t r = 0; r < seg.n_rounds; r += 2) {
+        g.round<0>();
+        g.round<1>();
+        dst[0] = g.keepA;
+        if (g.lane < 7) dst[32] = g.keepB;
+        dst += 39;
     }
 }
 

@@ -615,7 +615,8 @@ int pdsat_batch_fill(pdsat_batch* b) {
                 b->n_kernels++;
             }
         }
-        mt19937_bits_kernel<<<b->n_mt_segs, 256, 0, st>>>(b->d_mt_states, b->d_mt_segs, b->d_stream);
+        mt19937_bits_kernel<<<(b->n_mt_segs + MT_BITS_WARPS - 1) / MT_BITS_WARPS, MT_BITS_WARPS * 32, 0, st>>>(
+            b->d_mt_states, b->d_mt_segs, b->n_mt_segs, b->d_stream);
         b->n_kernels++;
     }
     if (b->has_explicit) {
@@ -907,7 +908,7 @@ int pdsat_mt19937_bool_rand(int device, uint32_t seed, uint64_t first, uint64_t 
     CU(cudaFuncSetAttribute(mt19937_jump_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MT_JUMP_SMEM));
     for (auto& l : launches)
         mt19937_jump_kernel<<<(unsigned)l.second, MT_JUMP_THREADS, MT_JUMP_SMEM>>>(d_polys, d_state, d_tasks + l.first);
-    mt19937_bits_kernel<<<n_segs, 256>>>(d_state, d_seg, d_out);
+    mt19937_bits_kernel<<<(n_segs + MT_BITS_WARPS - 1) / MT_BITS_WARPS, MT_BITS_WARPS * 32>>>(d_state, d_seg, n_segs, d_out);
     CU(cudaGetLastError());
     CU(cudaMemcpy(hbits.data(), d_out, words * 4, cudaMemcpyDeviceToHost));
     cudaFree(d_state);
