@@ -38,13 +38,34 @@ def needs_build() -> bool:
     return False
 
 
-def build(force: bool = False, verbose: bool = False, extra=()) -> str:
-    if not force and not needs_build():
-        return LIB
-    cmd = [find_nvcc()] + NVCC_FLAGS + list(extra) + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+HOST_DIR = os.path.join(HERE, "host")
+HOST_BIN = os.path.join(HERE, "pd-sat-b200")
+HOST_SOURCES = ["pd_sat_main.cpp", "dimacs.hpp", "predict.hpp"]
+
+
+def build_host(force: bool = False, verbose: bool = False) -> str:
+    """C++ host driver (reference-style CLI) linked against the C ABI only."""
+    stale = force or not os.path.exists(HOST_BIN) or any(
+        os.path.getmtime(os.path.join(HOST_DIR, f)) > os.path.getmtime(HOST_BIN) for f in HOST_SOURCES) or \
+        os.path.getmtime(LIB) > os.path.getmtime(HOST_BIN)
+    if not stale:
+        return HOST_BIN
+    cxx = shutil.which("g++") or "g++"
+    cmd = [cxx, "-O2", "-std=c++17", "-Wall", "-o", HOST_BIN, os.path.join(HOST_DIR, "pd_sat_main.cpp"),
+           "-L" + HERE, "-lpdsat_b200", "-Wl,-rpath,$ORIGIN"]
     if verbose:
         print(" ".join(cmd))
     subprocess.check_call(cmd)
+    return HOST_BIN
+
+
+def build(force: bool = False, verbose: bool = False, extra=()) -> str:
+    if force or needs_build():
+        cmd = [find_nvcc()] + NVCC_FLAGS + list(extra) + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+        if verbose:
+            print(" ".join(cmd))
+        subprocess.check_call(cmd)
+    build_host(force, verbose)
     return LIB
 
 

@@ -102,3 +102,19 @@ def main():
 
 if __name__ == "__main__":
     main()
+
+
+def odls_sample():
+    """Data fixture: the first 4 ODLS pairs of the reference's ODLS_10_pairs.txt."""
+    pairs = fx.parse_odls_pairs(open("/root/reference/src_common/ODLS_10_pairs.txt").read())
+    with open(os.path.join(HERE, "odls_pairs_sample.txt"), "w") as f:
+        f.write("# first 4 pairs of orthogonal diagonal Latin squares of order 10 from the reference's\n"
+                "# src_common/ODLS_10_pairs.txt (data fixture; written by tests/golden/make_golden.py)\n")
+        for a, b in pairs[:4]:
+            for ra, rb in zip(a, b):
+                f.write("".join(map(str, ra)) + " " + "".join(map(str, rb)) + "\n")
+            f.write("\n")
+
+
+if __name__ == "__main__":
+    odls_sample()
