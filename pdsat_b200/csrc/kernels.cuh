@@ -431,7 +431,7 @@ __device__ __forceinline__ uint64_t shfl_down64(uint64_t v, int d) {
            __shfl_down_sync(0xffffffffu, (uint32_t)v, d);
 }
 
-static constexpr int MAX_COUNT_BITS = 13;
+static constexpr int MAX_COUNT_BITS = 15;
 static constexpr int MULTI_POP = 8;  // queued literals processed per propagation round
 
 struct WarpAcc {

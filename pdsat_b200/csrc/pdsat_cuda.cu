@@ -161,7 +161,9 @@ static int sync_device_db(pdsat_db* db) {
     free_device_db(db);
     const int max_smem = 227 * 1024;
     int wpc = max_smem / warp_bytes;
-    if (wpc < 1) return fail(PDSAT_ERR_LIMIT, "assignment state of one sample group exceeds shared memory");
+    // wpc == 0: the planes of one 64-sample group do not fit in shared memory with the current
+    // level-0 assignment; evaluation is refused (PDSAT_ERR_LIMIT) until fixed assumptions
+    // shrink the live set
     if (wpc > 16) wpc = 16;  // __launch_bounds__(512)
     db->warps_per_cta = wpc;
     db->smem_bytes = wpc * warp_bytes;
@@ -313,6 +315,9 @@ int pdsat_batch_create(pdsat_db* db, int32_t n_points, const pdsat_point* points
     int rc = need_device(db);
     if (rc) return rc;
     if (!out || n_points <= 0 || !points) return fail(PDSAT_ERR_ARG, "pdsat_batch_create: bad argument");
+    if (db->warps_per_cta < 1)
+        return fail(PDSAT_ERR_LIMIT, "assignment state of one sample group exceeds shared memory (" +
+                                         std::to_string(db->host.n_live) + " live variables)");
     *out = nullptr;
     const HostDb& h = db->host;
     pdsat_batch* b = new pdsat_batch();
