@@ -133,37 +133,51 @@ struct MtSegment {
     uint32_t pad;
 };
 
-// One jump-ahead: states[dst] = g(A) states[src], g = polys[poly] (x^(624*2^t) mod phi as
-// 19968 bits).  out[w] = XOR over the set bits i of g of x[i + w], where x[0..623] is the
-// source window and x continues by the mt19937 recurrence (mt_jump.hpp).
+// One jump-ahead: state[dst] = g(A) state[src], g = polys[poly] (x^(624*2^t) mod phi as
+// 19968 bits): out[w] = XOR over the set bits i of g of x[i + w], where x[0..623] is the source
+// window and x continues by the mt19937 recurrence (mt_jump.hpp).
+// A state slot is stored as MT_PARTS partial vectors whose XOR is the state: a jump is split
+// over MT_PARTS CTAs, CTA q handling the polynomial bits [q*3328, (q+1)*3328) and writing
+// partial vector q of dst (no atomics, no zeroing; consumers XOR the parts on load).  This cuts
+// the latency of a level of the jump tree by ~6x, which matters because the first levels have
+// only 1, 2, 4 ... jumps.
 struct MtJumpTask {
     uint32_t src, dst, poly, pad;
 };
 
-static constexpr int MT_JUMP_SLICES = 6;      // the polynomial's 624 words are cut into 6 x 104
-static constexpr int MT_JUMP_SLICE_WORDS = 104;
+static constexpr int MT_PARTS = 6;            // CTAs per jump = partial vectors per state slot
+static constexpr int MT_JUMP_SLICE_WORDS = 104;  // polynomial words per CTA (624 / 6)
+static constexpr int MT_JUMP_SUB = 6;         // sub-slices inside a CTA (3 warps each)
 static constexpr int MT_JUMP_V = 8;           // output words per thread (register window)
-static constexpr int MT_JUMP_THREADS = MT_JUMP_SLICES * 96;  // 78 of every 96 threads carry outputs
+static constexpr int MT_JUMP_THREADS = MT_JUMP_SUB * 96;  // 78 of every 96 threads carry outputs
 static constexpr int MT_JUMP_ROUNDS = 34;     // 34 * 624 = 21216 >= 19968 + 8 + 623 words
-static constexpr int MT_JUMP_SMEM = (MT_JUMP_ROUNDS * 624 + 624) * 4;
+static constexpr int MT_JUMP_SMEM = (MT_JUMP_ROUNDS * 624 + MT_JUMP_SLICE_WORDS) * 4;
+
+__device__ __forceinline__ size_t mt_state_off(uint32_t slot, int part) {
+    return ((size_t)slot * MT_PARTS + part) * 624;
+}
 
 __global__ void __launch_bounds__(MT_JUMP_THREADS) mt19937_jump_kernel(const uint32_t* __restrict__ polys,
                                                                        uint32_t* __restrict__ states,
                                                                        const MtJumpTask* __restrict__ tasks) {
     extern __shared__ uint32_t jsm[];
-    uint32_t* x = jsm;                         // MT_JUMP_ROUNDS * 624 words of the sequence
-    uint32_t* g = jsm + MT_JUMP_ROUNDS * 624;  // 624 words of polynomial bits
+    uint32_t* x = jsm;                         // the sequence, as far as this slice needs it
+    uint32_t* g = jsm + MT_JUMP_ROUNDS * 624;  // this CTA's 104 words of polynomial bits
     const int tid = threadIdx.x;
-    const MtJumpTask t = tasks[blockIdx.x];
-    const uint32_t* src = states + (size_t)t.src * 624;
-    const uint32_t* gp = polys + (size_t)t.poly * 624;
+    const MtJumpTask t = tasks[blockIdx.x / MT_PARTS];
+    const int q = blockIdx.x % MT_PARTS;
     for (int i = tid; i < 624; i += MT_JUMP_THREADS) {
-        x[i] = src[i];
-        g[i] = gp[i];
+        uint32_t v = 0;
+#pragma unroll
+        for (int p = 0; p < MT_PARTS; p++) v ^= states[mt_state_off(t.src, p) + i];
+        x[i] = v;
     }
+    if (tid < MT_JUMP_SLICE_WORDS) g[tid] = polys[(size_t)t.poly * 624 + q * MT_JUMP_SLICE_WORDS + tid];
     __syncthreads();
-    // run the recurrence forward: x[n+624] = x[n+397] ^ twist(x[n], x[n+1])
-    for (int r = 0; r < MT_JUMP_ROUNDS - 1; r++) {
+    // run the recurrence forward: x[n+624] = x[n+397] ^ twist(x[n], x[n+1]); slice q reads
+    // x[0 .. (q+1)*3328 + 8 + 623]
+    const int rounds = ((q + 1) * MT_JUMP_SLICE_WORDS * 32 + MT_JUMP_V + 624 + 623) / 624;
+    for (int r = 0; r < rounds - 1; r++) {
         uint32_t* cur = x + r * 624;
         const int base[3] = {0, 227, 454};
         const int cnt[3] = {227, 227, 170};
@@ -177,42 +191,61 @@ __global__ void __launch_bounds__(MT_JUMP_THREADS) mt19937_jump_kernel(const uin
             __syncthreads();
         }
     }
-    // correlation: thread (slice q, tp) accumulates output words 8*tp .. 8*tp+7 over the
-    // polynomial bits of slice q, sliding an 8-word register window along the sequence
-    const int q = tid / 96, tp = tid % 96;
+    // correlation: thread (sub-slice s, tp) accumulates output words 8*tp .. 8*tp+7 over the
+    // polynomial words [sb, se) of this CTA's slice, sliding an 8-word register window
+    const int s = tid / 96, tp = tid % 96;
+    const int sb = (s * MT_JUMP_SLICE_WORDS) / MT_JUMP_SUB, se = ((s + 1) * MT_JUMP_SLICE_WORDS) / MT_JUMP_SUB;
     uint32_t acc[MT_JUMP_V];
 #pragma unroll
     for (int v = 0; v < MT_JUMP_V; v++) acc[v] = 0;
     if (tp < 78) {
         const int w0 = tp * MT_JUMP_V;
-        const int gw0 = q * MT_JUMP_SLICE_WORDS;
-        const uint32_t* xs = x + w0 + gw0 * 32;
+        const uint32_t* xs = x + w0 + (q * MT_JUMP_SLICE_WORDS + sb) * 32;
         uint32_t r[MT_JUMP_V];
 #pragma unroll
         for (int v = 0; v < MT_JUMP_V; v++) r[v] = xs[v];
-        for (int gi = 0; gi < MT_JUMP_SLICE_WORDS; gi++) {
-            const uint32_t gw = g[gw0 + gi];
-            const uint32_t* xw = xs + gi * 32 + MT_JUMP_V;
+        for (int gi = sb; gi < se; gi++) {
+            const uint32_t gw = g[gi];
+            const uint32_t* xw = xs + (gi - sb) * 32 + MT_JUMP_V;
+            // two polynomial bits per step; the bits are warp-uniform, so the 4-way switch is
+            // a uniform branch and a step costs at most ONE 3-input XOR per output word
 #pragma unroll
-            for (int b = 0; b < 32; b++) {
-                const uint32_t m = (uint32_t)((int32_t)(gw << (31 - b)) >> 31);
+            for (int b = 0; b < 32; b += 2) {
+                const uint32_t t0 = xw[b], t1 = xw[b + 1];  // words entering the window
+                switch ((gw >> b) & 3u) {
+                    case 1:
 #pragma unroll
-                for (int v = 0; v < MT_JUMP_V; v++) acc[v] ^= r[(b + v) % MT_JUMP_V] & m;
-                r[b % MT_JUMP_V] = xw[b];
+                        for (int v = 0; v < MT_JUMP_V; v++) acc[v] ^= r[(b + v) % MT_JUMP_V];
+                        break;
+                    case 2:
+#pragma unroll
+                        for (int v = 0; v < MT_JUMP_V; v++)
+                            acc[v] ^= v < MT_JUMP_V - 1 ? r[(b + 1 + v) % MT_JUMP_V] : t0;
+                        break;
+                    case 3:
+#pragma unroll
+                        for (int v = 0; v < MT_JUMP_V; v++)
+                            acc[v] ^= r[(b + v) % MT_JUMP_V] ^ (v < MT_JUMP_V - 1 ? r[(b + 1 + v) % MT_JUMP_V] : t0);
+                        break;
+                    default:
+                        break;
+                }
+                r[b % MT_JUMP_V] = t0;
+                r[(b + 1) % MT_JUMP_V] = t1;
             }
         }
     }
     __syncthreads();  // everyone is done reading x: reuse its head for the partial sums
     if (tp < 78) {
 #pragma unroll
-        for (int v = 0; v < MT_JUMP_V; v++) x[q * 624 + tp * MT_JUMP_V + v] = acc[v];
+        for (int v = 0; v < MT_JUMP_V; v++) x[s * 624 + tp * MT_JUMP_V + v] = acc[v];
     }
     __syncthreads();
     for (int w = tid; w < 624; w += MT_JUMP_THREADS) {
         uint32_t o = 0;
 #pragma unroll
-        for (int s = 0; s < MT_JUMP_SLICES; s++) o ^= x[s * 624 + w];
-        states[(size_t)t.dst * 624 + w] = o;
+        for (int ss = 0; ss < MT_JUMP_SUB; ss++) o ^= x[ss * 624 + w];
+        states[mt_state_off(t.dst, q) + w] = o;
     }
 }
 
@@ -234,19 +267,18 @@ struct MtWarp {
         if (IDX < 32) keepA = lane == IDX ? word : keepA;
         else keepB = lane == IDX - 32 ? word : keepB;
     }
-    template <int C, int ODD>
-    __device__ __forceinline__ void chunk() {
-        const uint32_t a = R[C];
-        uint32_t b, m;
+    // neighbours of chunk C: b = mt[k+1], m = mt[(k+397) % 624] for k = 32C + lane
+    template <int C>
+    __device__ __forceinline__ void gather(uint32_t& b, uint32_t& m) const {
         if (C < 19) {
-            const uint32_t v = lane >= 1 ? R[C] : R[C + 1];
+            const uint32_t v = lane >= 1 ? R[C] : R[(C + 1) % 20];
             b = __shfl_sync(0xffffffffu, v, (lane + 1) & 31);
         } else {  // k = 608..623: the last word pairs with the NEW mt[0]
             const uint32_t v = lane == 0 ? R[0] : R[19];
             b = __shfl_sync(0xffffffffu, v, (lane + 1) & 15);
         }
         if (C < 7) {  // k + 397 < 624: old words of chunks C+12, C+13
-            const uint32_t v = lane >= 13 ? R[C + 12] : R[(C + 13) % 20];
+            const uint32_t v = lane >= 13 ? R[(C + 12) % 20] : R[(C + 13) % 20];
             m = __shfl_sync(0xffffffffu, v, (lane + 13) & 31);
         } else if (C == 7) {  // straddles the wrap: old mt[621..623], then new mt[0..28]
             const uint32_t m_old = __shfl_sync(0xffffffffu, R[19], (lane + 13) & 31);
@@ -256,6 +288,10 @@ struct MtWarp {
             const uint32_t v = lane >= 29 ? R[(C + 12) % 20] : R[(C + 13) % 20];
             m = __shfl_sync(0xffffffffu, v, (lane + 29) & 31);
         }
+    }
+    template <int C, int ODD>
+    __device__ __forceinline__ void update(uint32_t b, uint32_t m) {
+        const uint32_t a = R[C];
         const uint32_t y = (a & 0x80000000u) | (b & 0x7fffffffu);
         const uint32_t nv = m ^ (y >> 1) ^ ((0u - (b & 1u)) & 0x9908b0dfu);
         R[C] = nv;
@@ -270,36 +306,60 @@ struct MtWarp {
             carry = w >> 16;
         }
     }
+    // The 20 chunks of a round go in three groups (0-6, 7-13, 14-19).  Inside a group no chunk
+    // needs another chunk's NEW words (mt[k+397] is >= 227 words away), so all shuffles of the
+    // group are issued first and their latencies overlap; the group's updates follow.
     template <int ODD>
     __device__ __forceinline__ void round() {
-        chunk<0, ODD>(); chunk<1, ODD>(); chunk<2, ODD>(); chunk<3, ODD>(); chunk<4, ODD>();
-        chunk<5, ODD>(); chunk<6, ODD>(); chunk<7, ODD>(); chunk<8, ODD>(); chunk<9, ODD>();
-        chunk<10, ODD>(); chunk<11, ODD>(); chunk<12, ODD>(); chunk<13, ODD>(); chunk<14, ODD>();
-        chunk<15, ODD>(); chunk<16, ODD>(); chunk<17, ODD>(); chunk<18, ODD>(); chunk<19, ODD>();
+        uint32_t b0, b1, b2, b3, b4, b5, b6, m0, m1, m2, m3, m4, m5, m6;
+        gather<0>(b0, m0); gather<1>(b1, m1); gather<2>(b2, m2); gather<3>(b3, m3);
+        gather<4>(b4, m4); gather<5>(b5, m5); gather<6>(b6, m6);
+        update<0, ODD>(b0, m0); update<1, ODD>(b1, m1); update<2, ODD>(b2, m2); update<3, ODD>(b3, m3);
+        update<4, ODD>(b4, m4); update<5, ODD>(b5, m5); update<6, ODD>(b6, m6);
+        gather<7>(b0, m0); gather<8>(b1, m1); gather<9>(b2, m2); gather<10>(b3, m3);
+        gather<11>(b4, m4); gather<12>(b5, m5); gather<13>(b6, m6);
+        update<7, ODD>(b0, m0); update<8, ODD>(b1, m1); update<9, ODD>(b2, m2); update<10, ODD>(b3, m3);
+        update<11, ODD>(b4, m4); update<12, ODD>(b5, m5); update<13, ODD>(b6, m6);
+        gather<14>(b0, m0); gather<15>(b1, m1); gather<16>(b2, m2); gather<17>(b3, m3);
+        gather<18>(b4, m4); gather<19>(b5, m5);
+        update<14, ODD>(b0, m0); update<15, ODD>(b1, m1); update<16, ODD>(b2, m2); update<17, ODD>(b3, m3);
+        update<18, ODD>(b4, m4); update<19, ODD>(b5, m5);
     }
 };
 
 static constexpr int MT_BITS_WARPS = 4;  // warps (= segments) per CTA
 
+// n_rounds (even) is the same for every segment and passed by value so that the loop trip
+// count is provably uniform (no divergence around the warp collectives); surplus warps of the
+// last CTA redo the last segment and skip the stores.
 __global__ void __launch_bounds__(MT_BITS_WARPS * 32) mt19937_bits_kernel(const uint32_t* __restrict__ states,
                                                                           const MtSegment* __restrict__ segs,
-                                                                          int n_segs, uint32_t* __restrict__ out) {
-    const int seg_i = blockIdx.x * MT_BITS_WARPS + (threadIdx.x >> 5);
-    if (seg_i >= n_segs) return;
-    const MtSegment seg = segs[seg_i];
+                                                                          int n_segs, uint32_t n_rounds,
+                                                                          uint32_t* __restrict__ out) {
+    const int seg_raw = blockIdx.x * MT_BITS_WARPS + (threadIdx.x >> 5);
+    const bool live = seg_raw < n_segs;
+    const MtSegment seg = segs[live ? seg_raw : n_segs - 1];
     MtWarp g;
     g.lane = threadIdx.x & 31;
-    const uint32_t* s0 = states + (size_t)seg.state_idx * 624;
 #pragma unroll
-    for (int c = 0; c < 20; c++) g.R[c] = (32 * c + g.lane < 624) ? s0[32 * c + g.lane] : 0u;
+    for (int c = 0; c < 20; c++) {
+        uint32_t v = 0;
+        if (32 * c + g.lane < 624) {
+#pragma unroll
+            for (int p = 0; p < MT_PARTS; p++) v ^= states[mt_state_off(seg.state_idx, p) + 32 * c + g.lane];
+        }
+        g.R[c] = v;
+    }
     g.carry = 0;
     g.keepA = g.keepB = 0;
     uint32_t* dst = out + seg.out_off + g.lane;
-    for (uint64_t r = 0; r < seg.n_rounds; r += 2) {
+    for (uint32_t r = 0; r < n_rounds; r += 2) {
         g.round<0>();
         g.round<1>();
-        dst[0] = g.keepA;
-        if (g.lane < 7) dst[32] = g.keepB;
+        if (live) {
+            dst[0] = g.keepA;
+            if (g.lane < 7) dst[32] = g.keepB;
+        }
         dst += 39;
     }
 }

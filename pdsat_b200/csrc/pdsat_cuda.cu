@@ -409,7 +409,7 @@ int pdsat_batch_create(pdsat_db* db, int32_t n_points, const pdsat_point* points
         int m = 1;
         while ((1ull << m) < per_seg) m++;
         b->mt_m = m;
-        uint32_t extra = (uint32_t)b->n_mt_points;
+        uint32_t extra = 2u * (uint32_t)b->n_mt_points;  // slots 2p, 2p+1: ping-pong pair of point p
         uint64_t seg = 0;
         for (auto& hp : b->pts) {
             if (hp.mode != PDSAT_MODE_RANDOM_MT19937) continue;
@@ -462,7 +462,7 @@ int pdsat_batch_create(pdsat_db* db, int32_t n_points, const pdsat_point* points
     if (out_flags & PDSAT_OUT_ASSIGN)
         CUB(cudaMalloc(&b->d_assign, sizeof(uint64_t) * groups * (size_t)(h.n_live > 0 ? 2 * h.n_live : 1)));
     if (b->n_mt_segs) {
-        CUB(cudaMalloc(&b->d_mt_states, sizeof(uint32_t) * 624 * b->n_mt_states));
+        CUB(cudaMalloc(&b->d_mt_states, sizeof(uint32_t) * 624 * MT_PARTS * b->n_mt_states));
         CUB(cudaMalloc(&b->d_mt_segs, sizeof(MtSegment) * b->n_mt_segs));
         CUB(cudaMallocHost(&b->h_mt_states, sizeof(uint32_t) * 624 * b->n_mt_points));
         CUB(cudaMallocHost(&b->h_mt_segs, sizeof(MtSegment) * b->n_mt_segs));
@@ -475,7 +475,7 @@ int pdsat_batch_create(pdsat_db* db, int32_t n_points, const pdsat_point* points
                 MtSegment& sg = b->h_mt_segs[hp.seg_base + j];
                 sg.out_off = hp.stream_off + (uint64_t)j * ((1ull << b->mt_m) / 2) * 39;
                 sg.n_rounds = 1ull << b->mt_m;
-                sg.state_idx = j == 0 ? hp.mt_index : hp.extra_base + j - 1;
+                sg.state_idx = j == 0 ? 2 * hp.mt_index : hp.extra_base + j - 1;  // j == 0 fixed up per fill
                 sg.pad = 0;
             }
         }
@@ -559,30 +559,40 @@ int pdsat_batch_fill(pdsat_batch* b) {
     CU(cudaEventRecord(b->ev[0], st));
     CU(cudaMemcpyAsync(b->d_points, b->h_points, sizeof(PointDev) * b->pts.size(), cudaMemcpyHostToDevice, st));
     if (b->n_mt_segs) {
-        // seed states -> slot mt_index; jump-ahead (mt_jump.hpp) places every other segment
+        // seed states -> part 0 of slot 2p (other parts zero); jump-ahead (mt_jump.hpp) places
+        // every other segment
         int max_poly = -1;
         for (auto& hp : b->pts) {
             if (hp.mode != PDSAT_MODE_RANDOM_MT19937) continue;
             mt19937_seed((uint32_t)hp.seed, b->h_mt_states + (size_t)hp.mt_index * 624);
         }
-        CU(cudaMemcpyAsync(b->d_mt_states, b->h_mt_states, sizeof(uint32_t) * 624 * b->n_mt_points,
-                           cudaMemcpyHostToDevice, st));
-        // launch plan: (a) per set bit t of the first round, in-place jumps by 2^t rounds;
-        // (b) binary tree over the segments, top level first
+        CU(cudaMemsetAsync(b->d_mt_states, 0, sizeof(uint32_t) * 624 * MT_PARTS * 2 * b->n_mt_points, st));
+        CU(cudaMemcpy2DAsync(b->d_mt_states, sizeof(uint32_t) * 624 * MT_PARTS * 2, b->h_mt_states, sizeof(uint32_t) * 624,
+                             sizeof(uint32_t) * 624, b->n_mt_points, cudaMemcpyHostToDevice, st));
+        // launch plan: (a) per set bit t of the first round, a jump by 2^t rounds between the
+        // point's two slots; (b) binary tree over the segments, top level first
         struct Launch { size_t off, cnt; };
         std::vector<Launch> launches;
         size_t nt = 0;
+        std::vector<uint32_t> cur_slot(b->pts.size());
+        for (size_t p = 0; p < b->pts.size(); p++) cur_slot[p] = 2 * b->pts[p].mt_index;
         for (int t = 0; t < 64; t++) {
             size_t start = nt;
-            for (auto& hp : b->pts) {
+            for (size_t p = 0; p < b->pts.size(); p++) {
+                HostPoint& hp = b->pts[p];
                 if (hp.mode != PDSAT_MODE_RANDOM_MT19937 || !((hp.mt_first_round >> t) & 1ull)) continue;
-                b->h_mt_tasks[nt++] = MtJumpTask{hp.mt_index, hp.mt_index, (uint32_t)t, 0};
+                const uint32_t other = cur_slot[p] ^ 1u;
+                b->h_mt_tasks[nt++] = MtJumpTask{cur_slot[p], other, (uint32_t)t, 0};
+                cur_slot[p] = other;
             }
             if (nt > start) {
                 launches.push_back({start, nt - start});
                 if (t > max_poly) max_poly = t;
             }
         }
+        for (size_t p = 0; p < b->pts.size(); p++)
+            if (b->pts[p].mode == PDSAT_MODE_RANDOM_MT19937) b->h_mt_segs[b->pts[p].seg_base].state_idx = cur_slot[p];
+        CU(cudaMemcpyAsync(b->d_mt_segs, b->h_mt_segs, sizeof(MtSegment) * b->n_mt_segs, cudaMemcpyHostToDevice, st));
         uint32_t max_segs = 0;
         for (auto& hp : b->pts)
             if (hp.mode == PDSAT_MODE_RANDOM_MT19937 && hp.n_segs > max_segs) max_segs = hp.n_segs;
@@ -591,10 +601,11 @@ int pdsat_batch_fill(pdsat_batch* b) {
         for (int lev = top; lev >= 0 && max_segs > 1; lev--) {
             size_t start = nt;
             const uint32_t stride = 1u << lev;
-            for (auto& hp : b->pts) {
+            for (size_t p = 0; p < b->pts.size(); p++) {
+                HostPoint& hp = b->pts[p];
                 if (hp.mode != PDSAT_MODE_RANDOM_MT19937) continue;
                 for (uint32_t j = 0; j + stride < hp.n_segs; j += 2 * stride) {
-                    const uint32_t src = j == 0 ? hp.mt_index : hp.extra_base + j - 1;
+                    const uint32_t src = j == 0 ? cur_slot[p] : hp.extra_base + j - 1;
                     const uint32_t dst = hp.extra_base + j + stride - 1;
                     b->h_mt_tasks[nt++] = MtJumpTask{src, dst, (uint32_t)(b->mt_m + lev), 0};
                 }
@@ -615,13 +626,13 @@ int pdsat_batch_fill(pdsat_batch* b) {
             }
             CU(cudaMemcpyAsync(b->d_mt_tasks, b->h_mt_tasks, sizeof(MtJumpTask) * nt, cudaMemcpyHostToDevice, st));
             for (auto& L : launches) {
-                mt19937_jump_kernel<<<(unsigned)L.cnt, MT_JUMP_THREADS, MT_JUMP_SMEM, st>>>(db->d_polys, b->d_mt_states,
+                mt19937_jump_kernel<<<(unsigned)L.cnt * MT_PARTS, MT_JUMP_THREADS, MT_JUMP_SMEM, st>>>(db->d_polys, b->d_mt_states,
                                                                                              b->d_mt_tasks + L.off);
                 b->n_kernels++;
             }
         }
         mt19937_bits_kernel<<<(b->n_mt_segs + MT_BITS_WARPS - 1) / MT_BITS_WARPS, MT_BITS_WARPS * 32, 0, st>>>(
-            b->d_mt_states, b->d_mt_segs, b->n_mt_segs, b->d_stream);
+            b->d_mt_states, b->d_mt_segs, b->n_mt_segs, 1u << b->mt_m, b->d_stream);
         b->n_kernels++;
     }
     if (b->has_explicit) {
@@ -882,25 +893,28 @@ int pdsat_mt19937_bool_rand(int device, uint32_t seed, uint64_t first, uint64_t 
     std::vector<MtJumpTask> tasks;
     std::vector<std::pair<size_t, size_t>> launches;
     int max_poly = -1;
+    uint32_t cur = 0;  // slots 0/1: ping-pong pair, slots 2..4: segments 1..3
     for (int t = 0; t < 64; t++)
         if ((r0 >> t) & 1ull) {
             launches.push_back({tasks.size(), 1});
-            tasks.push_back(MtJumpTask{0, 0, (uint32_t)t, 0});
+            tasks.push_back(MtJumpTask{cur, cur ^ 1u, (uint32_t)t, 0});
+            cur ^= 1u;
             max_poly = t;
         }
     launches.push_back({tasks.size(), 1});
-    tasks.push_back(MtJumpTask{0, 2, (uint32_t)(m + 1), 0});
+    tasks.push_back(MtJumpTask{cur, 3, (uint32_t)(m + 1), 0});
     launches.push_back({tasks.size(), 2});
-    tasks.push_back(MtJumpTask{0, 1, (uint32_t)m, 0});
-    tasks.push_back(MtJumpTask{2, 3, (uint32_t)m, 0});
+    tasks.push_back(MtJumpTask{cur, 2, (uint32_t)m, 0});
+    tasks.push_back(MtJumpTask{3, 4, (uint32_t)m, 0});
     if (m + 1 > max_poly) max_poly = m + 1;
     if (max_poly >= MAX_POLYS) return fail(PDSAT_ERR_LIMIT, "mt19937 stream offset too large");
     std::vector<MtSegment> segs(n_segs);
-    for (int j = 0; j < n_segs; j++) segs[j] = MtSegment{(uint64_t)j * (L / 2) * 39, L, (uint32_t)j, 0};
+    for (int j = 0; j < n_segs; j++) segs[j] = MtSegment{(uint64_t)j * (L / 2) * 39, L, j == 0 ? cur : (uint32_t)(j + 1), 0};
     uint32_t *d_state = nullptr, *d_out = nullptr, *d_polys = nullptr;
     MtSegment* d_seg = nullptr;
     MtJumpTask* d_tasks = nullptr;
-    CU(cudaMalloc(&d_state, 624 * 4 * n_segs));
+    CU(cudaMalloc(&d_state, 624 * 4 * MT_PARTS * 5));
+    CU(cudaMemset(d_state, 0, 624 * 4 * MT_PARTS * 5));
     CU(cudaMalloc(&d_seg, sizeof(MtSegment) * n_segs));
     CU(cudaMalloc(&d_out, words * 4));
     CU(cudaMalloc(&d_polys, (size_t)(max_poly + 1) * 624 * 4));
@@ -912,8 +926,8 @@ int pdsat_mt19937_bool_rand(int device, uint32_t seed, uint64_t first, uint64_t 
     CU(cudaMemcpy(d_tasks, tasks.data(), sizeof(MtJumpTask) * tasks.size(), cudaMemcpyHostToDevice));
     CU(cudaFuncSetAttribute(mt19937_jump_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MT_JUMP_SMEM));
     for (auto& l : launches)
-        mt19937_jump_kernel<<<(unsigned)l.second, MT_JUMP_THREADS, MT_JUMP_SMEM>>>(d_polys, d_state, d_tasks + l.first);
-    mt19937_bits_kernel<<<(n_segs + MT_BITS_WARPS - 1) / MT_BITS_WARPS, MT_BITS_WARPS * 32>>>(d_state, d_seg, n_segs, d_out);
+        mt19937_jump_kernel<<<(unsigned)l.second * MT_PARTS, MT_JUMP_THREADS, MT_JUMP_SMEM>>>(d_polys, d_state, d_tasks + l.first);
+    mt19937_bits_kernel<<<(n_segs + MT_BITS_WARPS - 1) / MT_BITS_WARPS, MT_BITS_WARPS * 32>>>(d_state, d_seg, n_segs, (uint32_t)L, d_out);
     CU(cudaGetLastError());
     CU(cudaMemcpy(hbits.data(), d_out, words * 4, cudaMemcpyDeviceToHost));
     cudaFree(d_state);
