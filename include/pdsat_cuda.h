@@ -97,7 +97,7 @@ typedef struct {
     int32_t warps_per_cta;   /* launch shape chosen for the BCP kernel                 */
     int32_t smem_bytes;      /* dynamic shared memory per CTA                          */
     int32_t grid;            /* CTAs launched                                          */
-    int32_t db_in_smem;      /* 1 = clause records staged in shared memory            */
+    int32_t db_in_smem;      /* 1 = occurrence offsets staged in shared memory (per CTA) */
     int32_t sm_count;
 } pdsat_db_info;
 

@@ -24,7 +24,8 @@ namespace pdsat {
 enum : uint8_t { LB_TRUE = 0, LB_FALSE = 1, LB_UNDEF = 2 };
 
 // unused literal slots hold the code of the pad plane (= 2*n_live, "always false")
-static constexpr uint16_t REC_CONT = 0xFFFE;  // slot 7: clause continues in the next record
+static constexpr uint16_t REC_CONT = 0xFFFE;      // slot 7: clause continues in the next record
+static constexpr uint16_t REC_INDIRECT = 0xFFFD;  // slot 7 of an inline record: slots 0-1 = index of the chain in rec
 static constexpr int REC_SLOTS = 8;           // uint16 slots per 16-byte record
 
 struct HostDb {
@@ -53,6 +54,7 @@ struct HostDb {
     std::vector<uint32_t> occ_off;        // 2*n_live + 1
     std::vector<uint32_t> occ;            // record index of each clause containing the literal
     std::vector<uint16_t> rec_len;        // clause length, indexed by its first record
+    std::vector<uint16_t> occrec;         // per literal (occ_off): the records themselves, inline
     int64_t n_rec = 0;
     int64_t n_clauses_live = 0;
     int64_t n_lits_live = 0;
@@ -178,6 +180,7 @@ struct HostDb {
         rec_len.clear();
         occ_off.assign((size_t)2 * n_live + 1, 0);
         occ.clear();
+        occrec.clear();
         n_rec = n_clauses_live = n_lits_live = 0;
         max_clause_len = 0;
         if (!base_ok) return;
@@ -227,6 +230,20 @@ struct HostDb {
         occ.resize(occ_pairs.size());
         std::vector<uint32_t> pos(occ_off.begin(), occ_off.end() - 1);
         for (auto& pr : occ_pairs) occ[pos[pr.first]++] = pr.second;
+        occrec.resize(occ.size() * REC_SLOTS);
+        for (size_t i = 0; i < occ.size(); i++) inline_record(occ[i], &occrec[i * REC_SLOTS]);
+    }
+
+    // the 16-byte record a list holds for the clause whose chain starts at rec[r]
+    void inline_record(uint32_t r, uint16_t* out) const {
+        if (rec_len[r] <= REC_SLOTS) {
+            memcpy(out, &rec[(size_t)r * REC_SLOTS], sizeof(uint16_t) * REC_SLOTS);
+        } else {
+            for (int s = 0; s < REC_SLOTS; s++) out[s] = 0;
+            out[0] = (uint16_t)(r & 0xFFFFu);
+            out[1] = (uint16_t)(r >> 16);
+            out[REC_SLOTS - 1] = REC_INDIRECT;
+        }
     }
 };
 

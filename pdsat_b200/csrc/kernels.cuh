@@ -20,9 +20,11 @@ namespace pdsat {
 
 // ------------------------------------------------------------------ device views
 struct DbDev {
-    const uint4* rec;         // 16-byte clause records: 8 x uint16 FALSE-plane codes
+    const uint4* rec;         // 16-byte clause records: 8 x uint16 FALSE-plane codes (chains for > 8 literals)
     const uint32_t* occ_off;  // [2*n_live+1]
-    const uint32_t* occ;      // first-record index of every clause containing the literal
+    const uint4* occrec;      // per literal: the RECORDS of the clauses containing it, inline
+                              // (a clause of > 8 literals appears as an indirect record -> rec[])
+    int32_t occ_off_in_smem;  // occ_off staged in shared memory (one copy per CTA)
     int32_t n_live;
     int32_t n_lit;            // 2*n_live
     int32_t n_base_assigned;
@@ -54,7 +56,7 @@ struct BatchDev {
     uint64_t n_groups;
     uint64_t n_words;
     const uint32_t* setcode;
-    const uint32_t* cand;       // candidate clause (first-record) ids, all points
+    const uint4* cand;          // first-wave candidate clause records, all points
     uint64_t* words;
     const uint32_t* stream;
     unsigned long long* cost;   // n_points * 8
@@ -398,31 +400,42 @@ __device__ __forceinline__ uint32_t rec_slot(const uint4& r, int j) {
 
 // ge1 / ge2 = samples in which the clause has >= 1 / >= 2 non-false literals.  A record has
 // 8 slots, each the code of a literal's FALSE plane; unused slots point at the "always false"
-// pad plane (all ones), so the evaluation is branch-free; slot 7 == REC_CONT chains a clause
-// longer than 8 literals into the next record.
-__device__ __forceinline__ void eval_clause(const uint4* __restrict__ rec, uint32_t ci, const uint64_t* S,
-                                            uint64_t& ge1, uint64_t& ge2) {
-    ge1 = 0;
-    ge2 = 0;
-    uint32_t cur = ci;
+// pad plane (all ones), so the evaluation is branch-free.  Occurrence lists and candidate lists
+// hold the records themselves (one dependent L2 load per clause instead of two); a clause of
+// more than 8 literals is an INDIRECT record (slot 7 == REC_INDIRECT, first word = index of
+// its chain in rec[], where slot 7 == REC_CONT links to the next record).
+static constexpr uint32_t REC_CONT_D = 0xFFFEu, REC_INDIRECT_D = 0xFFFDu;
+
+__device__ __forceinline__ void accumulate_slot(const uint64_t* S, uint32_t m, uint64_t& ge1, uint64_t& ge2) {
+    const uint64_t nf = ~S[m];
+    ge2 |= ge1 & nf;
+    ge1 |= nf;
+}
+
+__device__ __forceinline__ void eval_chain(const uint4* __restrict__ rec, uint32_t cur, const uint64_t* S,
+                                           uint64_t& ge1, uint64_t& ge2) {
     bool more;
     do {
         const uint4 r = __ldg(&rec[cur]);
 #pragma unroll
-        for (int j = 0; j < 7; j++) {
-            const uint64_t nf = ~S[rec_slot(r, j)];
-            ge2 |= ge1 & nf;
-            ge1 |= nf;
-        }
+        for (int j = 0; j < 7; j++) accumulate_slot(S, rec_slot(r, j), ge1, ge2);
         const uint32_t m7 = rec_slot(r, 7);
-        more = m7 == 0xFFFEu;
-        if (!more) {
-            const uint64_t nf = ~S[m7];
-            ge2 |= ge1 & nf;
-            ge1 |= nf;
-        }
+        more = m7 == REC_CONT_D;
+        if (!more) accumulate_slot(S, m7, ge1, ge2);
         cur++;
     } while (more);
+}
+
+__device__ __forceinline__ void eval_rec(const uint4& r, const uint4* __restrict__ rec, const uint64_t* S,
+                                         uint64_t& ge1, uint64_t& ge2) {
+    ge1 = 0;
+    ge2 = 0;
+    if (rec_slot(r, 7) == REC_INDIRECT_D) {
+        eval_chain(rec, r.x, S, ge1, ge2);
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; j++) accumulate_slot(S, rec_slot(r, j), ge1, ge2);
+    }
 }
 
 // make literal (plane m^1) true in the samples `imp` where it is still undefined
@@ -435,50 +448,53 @@ __device__ __forceinline__ void imply_lit(const WarpCtx& c, uint32_t m, uint64_t
     }
 }
 
-// rare path: in the samples of `unit` the clause has exactly one non-false literal; make it
-// true where it is still undefined (Solver.cc:641-648 uncheckedEnqueue(first, cr))
-__device__ __forceinline__ void imply_from_clause(const uint4* __restrict__ rec, uint32_t ci, const WarpCtx& c,
-                                                  uint64_t unit) {
-    uint32_t cur = ci;
-    bool more;
-    do {
-        const uint4 r = __ldg(&rec[cur]);
-#pragma unroll
-        for (int j = 0; j < 7; j++) {
-            const uint32_t m = rec_slot(r, j);
-            const uint64_t imp = unit & ~c.S[m];
-            if (imp) imply_lit(c, m, imp);
-        }
-        const uint32_t m7 = rec_slot(r, 7);
-        more = m7 == 0xFFFEu;
-        if (!more) {
-            const uint64_t imp = unit & ~c.S[m7];
-            if (imp) imply_lit(c, m7, imp);
-        }
-        cur++;
-    } while (more);
+__device__ __forceinline__ void imply_slot(const WarpCtx& c, uint32_t m, uint64_t unit) {
+    const uint64_t imp = unit & ~c.S[m];
+    if (imp) imply_lit(c, m, imp);
 }
 
-__device__ __forceinline__ void settle_clause(const uint4* __restrict__ rec, uint32_t ci, const WarpCtx& c,
-                                              uint64_t live, uint64_t ge1, uint64_t ge2) {
+// rare path: in the samples of `unit` the clause has exactly one non-false literal; make it
+// true where it is still undefined (Solver.cc:641-648 uncheckedEnqueue(first, cr))
+__device__ __forceinline__ void imply_from_rec(const uint4& r0, const uint4* __restrict__ rec, const WarpCtx& c,
+                                               uint64_t unit) {
+    if (rec_slot(r0, 7) == REC_INDIRECT_D) {
+        uint32_t cur = r0.x;
+        bool more;
+        do {
+            const uint4 r = __ldg(&rec[cur]);
+#pragma unroll
+            for (int j = 0; j < 7; j++) imply_slot(c, rec_slot(r, j), unit);
+            const uint32_t m7 = rec_slot(r, 7);
+            more = m7 == REC_CONT_D;
+            if (!more) imply_slot(c, m7, unit);
+            cur++;
+        } while (more);
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; j++) imply_slot(c, rec_slot(r0, j), unit);
+    }
+}
+
+__device__ __forceinline__ void settle_rec(const uint4& r, const uint4* __restrict__ rec, const WarpCtx& c,
+                                           uint64_t live, uint64_t ge1, uint64_t ge2) {
     const uint64_t confl = ~ge1 & live;
     const uint64_t unit = ge1 & ~ge2 & live;
     if (confl) atomicOr((unsigned long long*)c.dead, (unsigned long long)confl);
-    if (unit) imply_from_clause(rec, ci, c, unit);
+    if (unit) imply_from_rec(r, rec, c, unit);
 }
 
-// visit list[0..n): two clauses per lane per trip so that their loads overlap
-__device__ __forceinline__ void visit_list(const uint4* __restrict__ rec, const uint32_t* __restrict__ list,
-                                           uint32_t n, const WarpCtx& c, uint64_t live, int lane) {
+// visit the records list[0..n): two clauses per lane per trip so that their loads overlap
+__device__ __forceinline__ void visit_records(const uint4* __restrict__ rec, const uint4* __restrict__ list,
+                                              uint32_t n, const WarpCtx& c, uint64_t live, int lane) {
     for (uint32_t i = lane; i < n; i += 64) {
-        const uint32_t c0 = __ldg(&list[i]);
         const bool two = i + 32 < n;
-        const uint32_t c1 = two ? __ldg(&list[i + 32]) : c0;
+        const uint4 r0 = __ldg(&list[i]);
+        const uint4 r1 = __ldg(&list[two ? i + 32 : i]);
         uint64_t a1, a2, b1, b2;
-        eval_clause(rec, c0, c.S, a1, a2);
-        eval_clause(rec, c1, c.S, b1, b2);
-        settle_clause(rec, c0, c, live, a1, a2);
-        if (two) settle_clause(rec, c1, c, live, b1, b2);
+        eval_rec(r0, rec, c.S, a1, a2);
+        eval_rec(r1, rec, c.S, b1, b2);
+        settle_rec(r0, rec, c, live, a1, a2);
+        if (two) settle_rec(r1, rec, c, live, b1, b2);
     }
 }
 
@@ -542,6 +558,16 @@ bcp_kernel(DbDev db, BatchDev b, int warp_bytes, int qcap) {
     c.ntouched = c.qtail + 1;
     c.qmask = (uint32_t)qcap - 1;
 
+    // occurrence offsets: one copy per CTA in shared memory when it fits (saves a dependent L2
+    // round trip per propagation round)
+    const uint32_t* occ_off = db.occ_off;
+    if (db.occ_off_in_smem) {
+        uint32_t* so = (uint32_t*)(smem + (size_t)wpc * warp_bytes);
+        for (int i = threadIdx.x; i <= db.n_lit; i += blockDim.x) so[i] = db.occ_off[i];
+        __syncthreads();
+        occ_off = so;
+    }
+
     // the planes start clean and every group cleans up after itself
     for (int i = lane; i < n_planes; i += 32) c.S[i] = i == db.n_lit ? ~0ull : 0ull;  // plane n_lit = pad
     for (int i = lane; i < inq_words; i += 32) c.inq[i] = 0;
@@ -594,7 +620,7 @@ bcp_kernel(DbDev db, BatchDev b, int warp_bytes, int qcap) {
             // ---- (2) first wave over the point's candidate clauses
             if (pt->cand_cnt) {
                 const uint64_t live = valid & ~*(volatile uint64_t*)c.dead;
-                visit_list(db.rec, b.cand + pt->cand_off, pt->cand_cnt, c, live, lane);
+                visit_records(db.rec, b.cand + pt->cand_off, pt->cand_cnt, c, live, lane);
                 __syncwarp();
             }
 
@@ -614,8 +640,8 @@ bcp_kernel(DbDev db, BatchDev b, int warp_bytes, int qcap) {
                 if (lane < (int)np) {
                     atomicAnd(&c.inq[myl >> 5], ~(1u << (myl & 31)));
                     const uint32_t nl = myl ^ 1;  // this literal just became false somewhere
-                    mybeg = __ldg(&db.occ_off[nl]);
-                    mylen = __ldg(&db.occ_off[nl + 1]) - mybeg;
+                    mybeg = occ_off[nl];
+                    mylen = occ_off[nl + 1] - mybeg;
                 }
                 uint32_t cum = mylen;  // inclusive scan over the first MULTI_POP lanes
 #pragma unroll
@@ -641,13 +667,13 @@ bcp_kernel(DbDev db, BatchDev b, int warp_bytes, int qcap) {
                         if (i >= bound[q - 1]) o0 = base[q];
                         if (i1 >= bound[q - 1]) o1 = base[q];
                     }
-                    const uint32_t c0 = __ldg(&db.occ[o0 + i]);
-                    const uint32_t c1 = __ldg(&db.occ[o1 + i1]);
+                    const uint4 r0 = __ldg(&db.occrec[o0 + i]);
+                    const uint4 r1 = __ldg(&db.occrec[o1 + i1]);
                     uint64_t a1, a2, b1, b2;
-                    eval_clause(db.rec, c0, c.S, a1, a2);
-                    eval_clause(db.rec, c1, c.S, b1, b2);
-                    settle_clause(db.rec, c0, c, live, a1, a2);
-                    if (two) settle_clause(db.rec, c1, c, live, b1, b2);
+                    eval_rec(r0, db.rec, c.S, a1, a2);
+                    eval_rec(r1, db.rec, c.S, b1, b2);
+                    settle_rec(r0, db.rec, c, live, a1, a2);
+                    if (two) settle_rec(r1, db.rec, c, live, b1, b2);
                 }
                 __syncwarp();
             }

@@ -36,7 +36,7 @@ struct pdsat_db {
     // device copies
     uint4* d_rec = nullptr;
     uint32_t* d_occ_off = nullptr;
-    uint32_t* d_occ = nullptr;
+    uint4* d_occrec = nullptr;
     DbDev dev{};
     // launch shape
     int warps_per_cta = 0, warp_bytes = 0, qcap = 0, smem_bytes = 0, grid = 0;
@@ -73,7 +73,7 @@ struct pdsat_batch {
     // device
     PointDev* d_points = nullptr;
     uint32_t* d_setcode = nullptr;
-    uint32_t* d_cand = nullptr;
+    uint4* d_cand = nullptr;
     uint64_t* d_words = nullptr;
     uint32_t* d_stream = nullptr;
     unsigned long long* d_cost = nullptr;
@@ -126,10 +126,10 @@ static void free_device_db(pdsat_db* db) {
     if (db->device < 0) return;
     cudaFree(db->d_rec);
     cudaFree(db->d_occ_off);
-    cudaFree(db->d_occ);
+    cudaFree(db->d_occrec);
     db->d_rec = nullptr;
     db->d_occ_off = nullptr;
-    db->d_occ = nullptr;
+    db->d_occrec = nullptr;
 }
 
 static int count_bits_for(int n) {
@@ -160,25 +160,33 @@ static int sync_device_db(pdsat_db* db) {
     CU(cudaSetDevice(db->device));
     free_device_db(db);
     const int max_smem = 227 * 1024;
+    // occurrence offsets get one shared-memory copy per CTA if that costs at most one warp
+    const int occ_off_bytes = ((n_lit + 1) * 4 + 15) & ~15;
     int wpc = max_smem / warp_bytes;
+    int occ_in_smem = 0;
+    if (wpc >= 2 && occ_off_bytes <= warp_bytes) {
+        occ_in_smem = 1;
+        wpc = (max_smem - occ_off_bytes) / warp_bytes;
+    }
     // wpc == 0: the planes of one 64-sample group do not fit in shared memory with the current
     // level-0 assignment; evaluation is refused (PDSAT_ERR_LIMIT) until fixed assumptions
     // shrink the live set
     if (wpc > 16) wpc = 16;  // __launch_bounds__(512)
     db->warps_per_cta = wpc;
-    db->smem_bytes = wpc * warp_bytes;
+    db->smem_bytes = wpc * warp_bytes + (occ_in_smem ? occ_off_bytes : 0);
     db->grid = db->sm_count;
     size_t nrec = (size_t)h.n_rec;
     CU(cudaMalloc(&db->d_rec, (nrec ? nrec : 1) * sizeof(uint4)));
     CU(cudaMalloc(&db->d_occ_off, h.occ_off.size() * sizeof(uint32_t)));
-    CU(cudaMalloc(&db->d_occ, (h.occ.size() ? h.occ.size() : 1) * sizeof(uint32_t)));
+    CU(cudaMalloc(&db->d_occrec, (h.occ.size() ? h.occ.size() : 1) * sizeof(uint4)));
     if (nrec) CU(cudaMemcpy(db->d_rec, h.rec.data(), nrec * sizeof(uint4), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(db->d_occ_off, h.occ_off.data(), h.occ_off.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
     if (!h.occ.empty())
-        CU(cudaMemcpy(db->d_occ, h.occ.data(), h.occ.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(db->d_occrec, h.occrec.data(), h.occ.size() * sizeof(uint4), cudaMemcpyHostToDevice));
     db->dev.rec = db->d_rec;
     db->dev.occ_off = db->d_occ_off;
-    db->dev.occ = db->d_occ;
+    db->dev.occrec = db->d_occrec;
+    db->dev.occ_off_in_smem = occ_in_smem;
     db->dev.n_live = h.n_live;
     db->dev.n_lit = n_lit;
     db->dev.n_base_assigned = h.n_base_assigned;
@@ -248,7 +256,7 @@ int pdsat_db_get_info(const pdsat_db* db, pdsat_db_info* info) {
     info->warps_per_cta = db->warps_per_cta;
     info->smem_bytes = db->smem_bytes;
     info->grid = db->grid;
-    info->db_in_smem = 0;
+    info->db_in_smem = db->dev.occ_off_in_smem;
     info->sm_count = db->sm_count;
     return PDSAT_OK;
 }
@@ -444,7 +452,7 @@ int pdsat_batch_create(pdsat_db* db, int32_t n_points, const pdsat_point* points
     CUB(cudaMalloc(&b->d_points, sizeof(PointDev) * n_points));
     CUB(cudaMallocHost(&b->h_points, sizeof(PointDev) * n_points));
     CUB(cudaMalloc(&b->d_setcode, sizeof(uint32_t) * n_codes));
-    CUB(cudaMalloc(&b->d_cand, sizeof(uint32_t) * (n_cand ? n_cand : 1)));
+    CUB(cudaMalloc(&b->d_cand, sizeof(uint4) * (n_cand ? n_cand : 1)));
     CUB(cudaMalloc(&b->d_words, sizeof(uint64_t) * words));
     CUB(cudaMalloc(&b->d_stream, sizeof(uint32_t) * (stream_words ? stream_words : 1)));
     CUB(cudaMalloc(&b->d_cost, sizeof(unsigned long long) * PDSAT_COST_WORDS * n_points));
@@ -517,9 +525,11 @@ int pdsat_batch_create(pdsat_db* db, int32_t n_points, const pdsat_point* points
             pd.cand_cnt = (uint32_t)hp.cand.size();
             off += pd.k;
             codes.insert(codes.end(), hp.setcode.begin(), hp.setcode.end());
-            if (!hp.cand.empty())
-                CUB(cudaMemcpy(b->d_cand + hp.cand_off, hp.cand.data(), sizeof(uint32_t) * hp.cand.size(),
-                               cudaMemcpyHostToDevice));
+            if (!hp.cand.empty()) {
+                std::vector<uint16_t> recs(hp.cand.size() * REC_SLOTS);
+                for (size_t i = 0; i < hp.cand.size(); i++) h.inline_record(hp.cand[i], &recs[i * REC_SLOTS]);
+                CUB(cudaMemcpy(b->d_cand + hp.cand_off, recs.data(), sizeof(uint4) * hp.cand.size(), cudaMemcpyHostToDevice));
+            }
         }
         CUB(cudaMemcpy(b->d_setcode, codes.data(), sizeof(uint32_t) * n_codes, cudaMemcpyHostToDevice));
         CUB(cudaMemcpy(b->d_points, b->h_points, sizeof(PointDev) * n_points, cudaMemcpyHostToDevice));
