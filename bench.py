@@ -337,6 +337,50 @@ def run_ours(args):
                                     "models": int(found), "secret_found": bool(found >= 1 and expect in [int(x) for x in smp])}
         be.close()
         db2.close()
+        # tabu-search step (config 3 shape): centre {148..177} + its 177 Hamming-1 neighbours in
+        # ONE batch, per-point mt19937 streams (seed = 1 + point), through the public call sequence
+        from pdsat_b200 import predicter as pr
+        sets = [SET_VARS] + pr.hamming1_neighbourhood(SET_VARS, list(range(1, 178)))
+        n_pt = 200_000
+        bn = api.Batch(db, [api.Point(sv, n_pt, api.MODE_MT19937, seed=1 + i) for i, sv in enumerate(sets)])
+        bn.run()
+        torch.cuda.synchronize()
+        t_n = time.perf_counter()
+        for _ in range(3):
+            cn = bn.run()
+        t_n = (time.perf_counter() - t_n) / 3
+        fn, pn = bn.last_ms()
+        extra["tabu_neighbourhood_178pts"] = {"points": len(sets), "samples_per_point": n_pt, "e2e_ms": t_n * 1e3,
+                                              "fill_ms": fn, "propagate_ms": pn,
+                                              "samples_per_s_e2e": len(sets) * n_pt / t_n,
+                                              "points_per_s": len(sets) / t_n}
+        bn.close()
+        # ODLS order-10 pair CNF (config 5: clause DB >> shared memory, 10-literal clauses):
+        # 8 cells of square A get a random value each (one-hot over the cell's 10 variables)
+        from pdsat_b200 import fixtures as fx
+        onv, ocl = fx.odls_pair_cnf(10)
+        ooffs, olits = fx.to_csr(ocl)
+        odb = api.ClauseDb(onv, ooffs, olits, device=local_rank)
+        odb.set_stream(stream_t.cuda_stream)
+        cells = [(1, 1), (1, 2), (2, 3), (3, 4), (4, 6), (5, 7), (6, 8), (8, 9)]
+        ovars = [fx.odls_var(10, 0, i, j, z) for (i, j) in cells for z in range(10)]
+        n_o = 100_000
+        rng = np.random.default_rng(3)
+        pick = rng.integers(0, 10, size=(n_o, len(cells)))
+        vals = np.zeros((n_o, len(ovars)), dtype=np.uint8)
+        for ci in range(len(cells)):
+            vals[np.arange(n_o), ci * 10 + pick[:, ci]] = 1
+        bo = api.Batch(odb, [api.Point(ovars, n_o, api.MODE_EXPLICIT, explicit_values=vals)])
+        for _ in range(3):
+            co = bo.run()[0]
+        fo, po = bo.last_ms()
+        oi = odb.info()
+        extra["odls10_predict"] = {"samples": n_o, "set_size": len(ovars), "propagate_ms": po, "fill_ms": fo,
+                                   "samples_per_s": n_o / (po * 1e-3), "conflict_frac": co.n_conflict / n_o,
+                                   "mean_trail_conflict_free": co.sum_trail / max(1, n_o - co.n_conflict),
+                                   "warps_per_cta": oi.warps_per_cta, "clauses": int(oi.n_clauses_live)}
+        bo.close()
+        odb.close()
 
     t = torch.tensor([dev_ms, e2e_s * 1e3, float(kernel_ms)], dtype=torch.float64, device="cuda")
     if dist is not None:

@@ -94,4 +94,13 @@ inline Estimate estimate(const pdsat_cost& c, size_t k, const std::string& eval,
     return e;
 }
 
+// sample variance of the conflict-free samples' cost (WritePredictToFile,
+// mpi_predicter.cpp:2219-2224) from the integer sums; numerator exact in 128-bit integers
+inline double sample_variance(const pdsat_cost& c) {
+    const uint64_t n = c.n - c.n_conflict;
+    if (n < 2) return -1.0;
+    const unsigned __int128 num = (unsigned __int128)n * c.sumsq_trail - (unsigned __int128)c.sum_trail * c.sum_trail;
+    return (double)num / ((double)n * (double)(n - 1));
+}
+
 }  // namespace pdsat_host

@@ -112,6 +112,17 @@ def predict_from_cost(cost: api.Cost, k: int, evaluation_type: str = "propagatio
     return s, med, pred
 
 
+def sample_variance(cost: api.Cost) -> float:
+    """s^2 of the conflict-free samples' cost (WritePredictToFile, mpi_predicter.cpp:2219-2224:
+    sum (x - mean)^2 / (solved - 1)) from the integer sums: (n*Sxx - Sx^2) / (n*(n-1)), the
+    numerator evaluated exactly in integers."""
+    n = cost.n - cost.n_conflict
+    if n < 2:
+        return -1.0
+    num = n * cost.sumsq_trail - cost.sum_trail * cost.sum_trail
+    return float(num) / float(n * (n - 1))
+
+
 class Predicter:
     """Scores decomposition sets on one GPU (or one rank of a multi-GPU job)."""
 

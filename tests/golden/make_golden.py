@@ -116,5 +116,26 @@ def odls_sample():
             f.write("\n")
 
 
+def rc2_golden():
+    """Solver::gen_valid_assumptions_rc2 (Solver.cc:1293-1435) run by the reference itself on
+    the weakened-Bivium cubes of SURVEY.md 8c-2b: template + keystream + the first N state bits
+    as units, enumerate the last k state variables (d_set ascending, d_set[0] most significant,
+    start = all negative)."""
+    nv, cl, _ = fx.bivium_template()
+    offs, lits = fx.to_csr(cl)
+    secret, stream = keystream_lits(0)
+    out = {}
+    for n_fixed, k in ((161, 16), (100, 14), (60, 12), (150, 10), (85, 12), (90, 12)):
+        R = orc.Oracle(nv, offs, lits, "ref")
+        R.add_units(stream + [2 * v + (0 if secret[v] else 1) for v in range(n_fixed)])
+        d_set = list(range(178 - k, 178))
+        valid, rows = R.rc2(d_set, [0] * k, 1 << k, 1 << k)
+        out["n%d_k%d_valid" % (n_fixed, k)] = np.asarray([valid], dtype=np.int64)
+        out["n%d_k%d_rows" % (n_fixed, k)] = np.packbits(rows.astype(np.uint8), axis=1)
+        print("rc2 N=%d k=%d survivors %d" % (n_fixed, k, valid))
+    np.savez_compressed(os.path.join(HERE, "rc2_golden.npz"), **out)
+
+
 if __name__ == "__main__":
     odls_sample()
+    rc2_golden()

@@ -109,3 +109,12 @@ def test_samples_for_set_and_schemas():
     assert pr.schema_vars("bivium_Beginning1", 30) == list(range(1, 31))
     nb = pr.hamming1_neighbourhood(list(range(148, 178)), list(range(1, 178)))
     assert len(nb) == 177 and sorted(len(s) for s in nb) == [29] * 30 + [31] * 147
+
+
+def test_sample_variance_from_integer_sums(oracle_mod):
+    from pdsat_b200 import api, predicter as pr
+    rng = np.random.default_rng(2)
+    x = rng.integers(230, 778, size=5000)
+    c = api.Cost(len(x), 0, 0, int(x.sum()), int((x.astype(np.int64) ** 2).sum()), 0)
+    ref = oracle_mod.sample_variance(x.astype(np.float64))
+    assert abs(pr.sample_variance(c) - ref) <= 1e-12 * ref

@@ -329,3 +329,29 @@ def test_gpu_random_cnfs(seed, oracle_mod, cuda_lib):
     for m in models:
         for cl in clauses:
             assert any((m[abs(l) - 1] == 1) == (l > 0) for l in cl)
+
+
+@pytest.mark.parametrize("case", ["n161_k16", "n100_k14", "n60_k12", "n150_k10", "n85_k12", "n90_k12"])
+def test_gpu_enumeration_matches_reference_rc2(case, bivium, golden, cuda_lib):
+    """SURVEY.md 8 a-10: the survivors of Solver::gen_valid_assumptions_rc2 (golden vectors
+    produced by the reference itself, tests/golden/make_golden.py) are exactly the assignments
+    the device enumeration leaves conflict-free.  rc2 orders with d_set[0] most significant and
+    negative literal = 0; ENUM mode has bit r <-> set_vars[r], so the index is bit-reversed."""
+    import os
+    from pdsat_b200 import api
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "rc2_golden.npz"))
+    n_fixed, k = (int(x[1:]) for x in case.split("_"))
+    valid = int(g[case + "_valid"][0])
+    rows = np.unpackbits(g[case + "_rows"], axis=1)[:, :k]
+    nv, _, offs, lits = bivium
+    secret = golden["secret"]
+    db = api.ClauseDb(nv, offs, lits, device=0)
+    db.set_fixed_assumptions(list(golden["stream_lits"]) + [2 * v + (0 if secret[v] else 1) for v in range(n_fixed)])
+    d_set = list(range(178 - k, 178))
+    b = api.Batch(db, [api.Point(d_set, 1 << k, api.MODE_ENUM)], api.OUT_FLAGS)
+    c = b.run()[0]
+    conflict, full = b.flags(0)
+    assert c.n - c.n_conflict == valid == len(rows)
+    survivors = set(int(i) for i in np.nonzero(~conflict)[0])
+    expect = set(sum(int(r[j]) << j for j in range(k)) for r in rows)
+    assert survivors == expect
