@@ -132,7 +132,18 @@ def rc2_golden():
         valid, rows = R.rc2(d_set, [0] * k, 1 << k, 1 << k)
         out["n%d_k%d_valid" % (n_fixed, k)] = np.asarray([valid], dtype=np.int64)
         out["n%d_k%d_rows" % (n_fixed, k)] = np.packbits(rows.astype(np.uint8), axis=1)
-        print("rc2 N=%d k=%d survivors %d" % (n_fixed, k, valid))
+        # the same cube assignment by assignment through the reference's propagate()
+        # (index bit j <-> d_set[j]); rc2 itself over-reports on some cubes, see DESIGN.md
+        R2 = orc.Oracle(nv, offs, lits, "ref")
+        R2.add_units(stream + [2 * v + (0 if secret[v] else 1) for v in range(n_fixed)])
+        surv = []
+        for idx in range(1 << k):
+            a = [2 * (v - 1) + (0 if (idx >> j) & 1 else 1) for j, v in enumerate(d_set)]
+            r, _ = R2.bcp(a, want_assigns=False)
+            if not r.conflict:
+                surv.append(idx)
+        out["n%d_k%d_bcp_survivors" % (n_fixed, k)] = np.asarray(surv, dtype=np.int64)
+        print("rc2 N=%d k=%d: rc2 reports %d, propagate() leaves %d" % (n_fixed, k, valid, len(surv)))
     np.savez_compressed(os.path.join(HERE, "rc2_golden.npz"), **out)
 
 

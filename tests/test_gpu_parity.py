@@ -332,17 +332,22 @@ def test_gpu_random_cnfs(seed, oracle_mod, cuda_lib):
 
 
 @pytest.mark.parametrize("case", ["n161_k16", "n100_k14", "n60_k12", "n150_k10", "n85_k12", "n90_k12"])
-def test_gpu_enumeration_matches_reference_rc2(case, bivium, golden, cuda_lib):
-    """SURVEY.md 8 a-10: the survivors of Solver::gen_valid_assumptions_rc2 (golden vectors
-    produced by the reference itself, tests/golden/make_golden.py) are exactly the assignments
-    the device enumeration leaves conflict-free.  rc2 orders with d_set[0] most significant and
-    negative literal = 0; ENUM mode has bit r <-> set_vars[r], so the index is bit-reversed."""
+def test_gpu_enumeration_vs_reference_cube(case, bivium, golden, cuda_lib):
+    """solve-mode enumeration of a cube.  Golden vectors come from the
+    reference itself (tests/golden/make_golden.py): (1) every assignment of the cube through the
+    reference's propagate() - the device must leave exactly those conflict-free; (2) the list
+    reported by Solver::gen_valid_assumptions_rc2.  rc2 equals (1) on the cubes SURVEY.md checked,
+    but on cubes with deep conflicts it OVER-reports (after a conflict below the last level it
+    flips a deeper assumption without undoing the conflicting level, Solver.cc:1399-1423, so the
+    pending conflict is never seen again): there it must still contain every true survivor.
+    rc2 orders with d_set[0] most significant; ENUM mode has bit r <-> set_vars[r]."""
     import os
     from pdsat_b200 import api
     g = np.load(os.path.join(os.path.dirname(__file__), "golden", "rc2_golden.npz"))
     n_fixed, k = (int(x[1:]) for x in case.split("_"))
-    valid = int(g[case + "_valid"][0])
+    rc2_valid = int(g[case + "_valid"][0])
     rows = np.unpackbits(g[case + "_rows"], axis=1)[:, :k]
+    bcp_surv = set(int(x) for x in g[case + "_bcp_survivors"])
     nv, _, offs, lits = bivium
     secret = golden["secret"]
     db = api.ClauseDb(nv, offs, lits, device=0)
@@ -351,7 +356,9 @@ def test_gpu_enumeration_matches_reference_rc2(case, bivium, golden, cuda_lib):
     b = api.Batch(db, [api.Point(d_set, 1 << k, api.MODE_ENUM)], api.OUT_FLAGS)
     c = b.run()[0]
     conflict, full = b.flags(0)
-    assert c.n - c.n_conflict == valid == len(rows)
     survivors = set(int(i) for i in np.nonzero(~conflict)[0])
-    expect = set(sum(int(r[j]) << j for j in range(k)) for r in rows)
-    assert survivors == expect
+    assert survivors == bcp_surv and c.n - c.n_conflict == len(bcp_surv)
+    rc2 = set(sum(int(r[j]) << j for j in range(k)) for r in rows)
+    assert len(rc2) == rc2_valid and survivors <= rc2
+    if case in ("n161_k16", "n100_k14", "n60_k12", "n150_k10"):
+        assert survivors == rc2

@@ -105,3 +105,24 @@ def test_estimator_restatement(oracle_mod):
     assert s == 230000.0 and float(med) == 230.0 and float(pred) == 230.0 * 2 ** 30
     assert float(oracle_mod.predict_prep(5, 1000, 30)) == 1e308       # 0.5 % is not enough
     assert float(oracle_mod.predict_prep(6, 1000, 30)) == 2.0 ** 30 * 3.0 / 0.006
+
+
+@pytest.mark.parametrize("case", ["n161_k16", "n100_k14", "n60_k12", "n85_k12", "n90_k12"])
+def test_port_cube_enumeration_matches_reference_propagate(case, bivium, golden, oracle_mod):
+    """Solve-mode cube, assignment by assignment (order of src_mpi/mpi_base.cpp:148-169): the C
+    restatement leaves exactly the assignments the reference's propagate() leaves
+    (tests/golden/rc2_golden.npz, *_bcp_survivors)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "rc2_golden.npz"))
+    n_fixed, k = (int(x[1:]) for x in case.split("_"))
+    nv, _, offs, lits = bivium
+    secret = golden["secret"]
+    P = oracle_mod.Oracle(nv, offs, lits, "port")
+    P.add_units(list(golden["stream_lits"]) + [2 * v + (0 if secret[v] else 1) for v in range(n_fixed)])
+    d_set = list(range(178 - k, 178))
+    surv = []
+    for idx in range(1 << k):
+        r, _ = P.bcp(oracle_mod.enum_assumptions(d_set, idx), want_assigns=False)
+        if not r.conflict:
+            surv.append(idx)
+    assert surv == [int(x) for x in g[case + "_bcp_survivors"]]
