@@ -241,6 +241,29 @@ def run_ours(args):
     cost_t = torch.zeros(api.COST_WORDS, dtype=torch.int64, device="cuda")
     batch.set_cost_buffer(cost_t.data_ptr())
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    # N > 1: the per-point cost all-reduce is fused into the BCP kernel over NVLink peer memory
+    # (CUDA IPC handles exchanged once through torch.distributed); --reduce nccl keeps the
+    # separate NCCL all-reduce for comparison
+    reduce_mode = "none"
+    if dist is not None:
+        reduce_mode = "nccl"
+        if args.reduce == "peer":
+            try:
+                mine = torch.frombuffer(bytearray(batch.peer_export()), dtype=torch.uint8).cuda()
+                allh = [torch.empty(64, dtype=torch.uint8, device="cuda") for _ in range(world)]
+                dist.all_gather(allh, mine)
+                batch.peer_connect([bytes(h.cpu().numpy().tobytes()) for h in allh], rank)
+                reduce_mode = "peer"
+            except Exception as e:  # IPC unavailable: fall back to NCCL, and say so
+                if rank == 0:
+                    print("peer reduce unavailable (%s); using NCCL all-reduce" % e, file=sys.stderr)
+        ok = torch.tensor([1 if reduce_mode == "peer" else 0], device="cuda")
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if reduce_mode == "peer" and int(ok.item()) == 0:
+            batch.peer_disconnect()
+            reduce_mode = "nccl"
+        dist.barrier()
+    use_nccl = reduce_mode == "nccl"
 
     def barrier():
         if dist is not None:
@@ -256,7 +279,7 @@ def run_ours(args):
     for w in range(args.warmup):
         flush.zero_()
         batch.propagate()
-        if dist is not None:
+        if use_nccl:
             dist.all_reduce(cost_t)
     barrier()
     sampler.start()
@@ -266,7 +289,7 @@ def run_ours(args):
         flush.zero_()
         ev[s][0].record()
         batch.propagate()
-        if dist is not None:
+        if use_nccl:
             dist.all_reduce(cost_t)
         ev[s][1].record()
     barrier()
@@ -281,27 +304,38 @@ def run_ours(args):
     # ---------------- e2e: public call sequence, host descriptors in, costs out
     for w in range(max(1, args.warmup // 2)):
         batch.reseed(0, seed0 + 7919 * (w + 1), first)
-        batch.run()
+        batch.fill()
+        batch.propagate()
+        if use_nccl:
+            dist.all_reduce(cost_t)
+        batch.costs()
     barrier()
     t0 = time.perf_counter()
     for s in range(args.steps):
         batch.reseed(0, seed0 + 104729 * (s + 1), first)
         batch.fill()
         batch.propagate()
-        if dist is not None:
+        if use_nccl:
             dist.all_reduce(cost_t)
         c = batch.costs()[0]
     barrier()
     e2e_s = time.perf_counter() - t0
+    n_reduced_check = c.n
     fill_ms_last, _ = batch.last_ms()
     # the timed regions above last milliseconds; keep the same fill+propagate load running for
     # ~1.5 s more so that nvidia-smi (100 ms period) sees the clocks under this load
     t_probe = time.perf_counter()
-    while time.perf_counter() - t_probe < 1.5:
+    probe_iters = torch.tensor([0], device="cuda")
+    while True:  # same number of (collective) propagate calls on every rank
         for _ in range(20):
             batch.fill()
             batch.propagate()
         torch.cuda.synchronize()
+        probe_iters[0] = 1 if time.perf_counter() - t_probe < 1.5 else 0
+        if dist is not None:
+            dist.all_reduce(probe_iters, op=dist.ReduceOp.MIN)
+        if int(probe_iters.item()) == 0:
+            break
     clocks = sampler.stop()
     clocks["note"] = "sampled across the timed regions plus 1.5 s of the same fill+propagate load"
 
@@ -428,7 +462,8 @@ def run_ours(args):
             "clocks": clocks,
             "kernel_ms_last": kernel_ms, "fill_ms_last": fill_ms_last, "wall_ms_per_step": 1e3 * t_wall / args.steps,
             "check": {"n": int(n_total_check), "n_conflict": int(costs_host.n_conflict),
-                      "sum_trail": int(costs_host.sum_trail)},
+                      "sum_trail": int(costs_host.sum_trail), "n_after_reduce": int(n_reduced_check)},
+            "reduce": reduce_mode,
             "extra": extra,
             "launch": {"grid": info.grid, "warps_per_cta": info.warps_per_cta, "smem_bytes": info.smem_bytes,
                        "live_vars": info.n_live_vars, "live_clauses": info.n_clauses_live},
@@ -458,6 +493,8 @@ def main():
     ap.add_argument("--cpu-samples", type=int, default=1500, help="CPU-arm samples per core per step")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the secondary workloads")
+    ap.add_argument("--reduce", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: fused NVLink peer-memory reduce (default) or NCCL all-reduce")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

@@ -164,6 +164,18 @@ int pdsat_batch_cost_device_ptr(pdsat_batch* b, void** dptr);
 int pdsat_batch_set_cost_buffer(pdsat_batch* b, void* dptr);
 int pdsat_batch_costs(pdsat_batch* b, pdsat_cost* out /* n_points */);
 
+/* Multi-GPU, one process per GPU: cost all-reduce FUSED into the BCP kernel over NVLink peer
+ * memory instead of a separate collective.  Every rank exports a 64-byte CUDA IPC handle of its
+ * reduce buffer, the ranks exchange the handles out of band (all_gather of 64 bytes), every
+ * rank connects; from then on pdsat_batch_propagate is COLLECTIVE (all ranks must call it the
+ * same number of times) and leaves the summed accumulators of ALL ranks in the cost buffer.
+ * Replaces the ncclAllReduce of SURVEY.md 8(e); results are identical (integer sums). */
+#define PDSAT_IPC_HANDLE_BYTES 64
+int pdsat_batch_peer_export(pdsat_batch* b, void* handle_out /* 64 bytes */);
+int pdsat_batch_peer_connect(pdsat_batch* b, int32_t n_ranks, int32_t my_rank,
+                             const void* handles /* n_ranks * 64 bytes, rank order */);
+int pdsat_batch_peer_disconnect(pdsat_batch* b);
+
 /* ---- per-sample results (optional outputs) ------------------------------------------- */
 /* bit s%64 of word s/64 (s counted inside the point) */
 int pdsat_batch_flags(pdsat_batch* b, int32_t point, uint64_t* conflict_bits, uint64_t* full_bits);

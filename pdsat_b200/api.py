@@ -28,7 +28,8 @@ EXPORTS = [
     "pdsat_batch_sync", "pdsat_batch_last_ms", "pdsat_batch_launch_count", "pdsat_batch_cost_device_ptr",
     "pdsat_batch_set_cost_buffer", "pdsat_batch_costs", "pdsat_batch_flags", "pdsat_batch_trail",
     "pdsat_batch_assign", "pdsat_batch_models", "pdsat_batch_destroy", "pdsat_eval_batch",
-    "pdsat_mt19937_bool_rand",
+    "pdsat_mt19937_bool_rand", "pdsat_batch_peer_export", "pdsat_batch_peer_connect",
+    "pdsat_batch_peer_disconnect",
 ]
 
 
@@ -96,6 +97,9 @@ def lib():
     L.pdsat_batch_destroy.restype = None
     L.pdsat_eval_batch.argtypes = [C.c_void_p, C.c_int32, C.POINTER(CPoint), C.POINTER(CCost)]
     L.pdsat_mt19937_bool_rand.argtypes = [C.c_int, C.c_uint32, C.c_uint64, C.c_uint64, C.c_void_p]
+    L.pdsat_batch_peer_export.argtypes = [C.c_void_p, C.c_void_p]
+    L.pdsat_batch_peer_connect.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
+    L.pdsat_batch_peer_disconnect.argtypes = [C.c_void_p]
     _lib = L
     return L
 
@@ -260,6 +264,21 @@ class Batch:
 
     def set_cost_buffer(self, dptr: int) -> None:
         _check(lib().pdsat_batch_set_cost_buffer(self.h, C.c_void_p(dptr)))
+
+    def peer_export(self) -> bytes:
+        """64-byte CUDA IPC handle of this rank's reduce buffer (exchange it with all ranks)."""
+        buf = C.create_string_buffer(64)
+        _check(lib().pdsat_batch_peer_export(self.h, buf))
+        return buf.raw
+
+    def peer_connect(self, handles: Sequence[bytes], my_rank: int) -> None:
+        """After this, propagate() is collective and leaves the all-rank sums in the cost buffer."""
+        blob = b"".join(handles)
+        assert len(blob) == 64 * len(handles)
+        _check(lib().pdsat_batch_peer_connect(self.h, len(handles), my_rank, blob))
+
+    def peer_disconnect(self) -> None:
+        _check(lib().pdsat_batch_peer_disconnect(self.h))
 
     def costs(self) -> List[Cost]:
         out = (CCost * len(self.points))()

@@ -50,6 +50,22 @@ struct PointDev {
 
 static constexpr uint32_t SETCODE_FIXED = 0x80000000u;  // set var already assigned at level 0; bit0 = its lbool
 
+// Multi-GPU cost reduce fused into the BCP kernel.  Every rank owns a small buffer that its
+// peers map through CUDA IPC: shared[parity][n_words] accumulators + done[parity] counters.
+// The last CTA of a rank's kernel adds the rank's per-point sums into EVERY rank's buffer with
+// system-scope atomics over NVLink and then signals done[parity] on every rank; a one-CTA
+// kernel on each rank waits for n_ranks signals and copies the all-reduced sums out.  Buffers
+// alternate by step parity, so a rank that runs ahead never touches the buffer a slower rank
+// is still reading (it cannot get two steps ahead: its own wait needs the slower rank's step).
+static constexpr int MAX_PEERS = 16;
+struct PeerDev {
+    unsigned long long* shared[MAX_PEERS];  // rank r's buffer as mapped in this process
+    unsigned int* cta_done;                 // local ticket counter (last-CTA detection)
+    int32_t n_ranks;
+    int32_t parity;
+    int32_t n_words;                        // accumulators per parity = n_points * 8
+};
+
 struct BatchDev {
     const PointDev* points;
     int32_t n_points;
@@ -70,6 +86,8 @@ struct BatchDev {
     uint64_t* model_sample;
     int32_t max_models;
     int32_t model_words;
+    // fused cost all-reduce over NVLink peer memory (0 ranks = off, see PeerDev)
+    PeerDev peer;
 };
 
 __device__ __forceinline__ int find_point(const PointDev* pts, int n, uint64_t g) {
@@ -803,6 +821,47 @@ bcp_kernel(DbDev db, BatchDev b, int warp_bytes, int qcap) {
         __syncwarp();
     }
     flush_acc(acc, b.cost, lane);
+
+    if (b.peer.n_ranks > 0) {
+        // last CTA of this rank pushes the rank's sums to every peer (itself included)
+        __shared__ unsigned int s_ticket;
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) s_ticket = atomicAdd(b.peer.cta_done, 1u);
+        __syncthreads();
+        if (s_ticket == gridDim.x - 1) {
+            __threadfence();
+            const int nw = b.peer.n_words;
+            for (int i = threadIdx.x; i < nw; i += blockDim.x) {
+                const unsigned long long v = __ldcg(&b.cost[i]);
+                if (v)
+                    for (int r = 0; r < b.peer.n_ranks; r++)
+                        atomicAdd_system(&b.peer.shared[r][(size_t)b.peer.parity * nw + i], v);
+            }
+            __threadfence_system();
+            __syncthreads();
+            if (threadIdx.x < b.peer.n_ranks)
+                atomicAdd_system(&b.peer.shared[threadIdx.x][(size_t)2 * nw + b.peer.parity], 1ull);
+            if (threadIdx.x == 0) *b.peer.cta_done = 0;
+        }
+    }
+}
+
+// One CTA per rank: wait until all ranks have pushed their sums for this step, publish the
+// all-reduced accumulators and clear the parity buffer for its next use (two steps later).
+__global__ void peer_wait_kernel(unsigned long long* shared, int n_words, int parity, unsigned long long target,
+                                 unsigned long long* cost_out) {
+    volatile unsigned long long* done = shared + (size_t)2 * n_words + parity;
+    if (threadIdx.x == 0) {
+        while (*done < target) __nanosleep(200);
+        __threadfence_system();
+    }
+    __syncthreads();
+    unsigned long long* buf = shared + (size_t)parity * n_words;
+    for (int i = threadIdx.x; i < n_words; i += blockDim.x) {
+        cost_out[i] = *((volatile unsigned long long*)&buf[i]);
+        buf[i] = 0;
+    }
 }
 
 }  // namespace pdsat

@@ -102,6 +102,12 @@ struct pdsat_batch {
     uint32_t* h_stream = nullptr;
     bool has_explicit = false;
     PointDev* h_points = nullptr;  // pinned mirror
+    // fused peer reduce (multi-GPU)
+    unsigned long long* d_peer_own = nullptr;          // this rank's IPC-exported buffer
+    unsigned long long* peer_ptr[MAX_PEERS] = {};      // every rank's buffer as mapped here
+    unsigned int* d_cta_done = nullptr;
+    int peer_ranks = 0, peer_me = 0;
+    uint64_t peer_step = 0;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     bool filled = false, propagated = false;
     int64_t n_kernels = 0;
@@ -702,8 +708,23 @@ int pdsat_batch_propagate(pdsat_batch* b) {
     uint64_t ctas_needed = (b->n_groups + db->warps_per_cta - 1) / db->warps_per_cta;
     int grid = (int)(ctas_needed < (uint64_t)db->grid ? ctas_needed : (uint64_t)db->grid);
     if (grid < 1) grid = 1;
+    const int n_cost_words = PDSAT_COST_WORDS * (int)b->pts.size();
+    const int parity = (int)(b->peer_step & 1);
+    if (b->peer_ranks > 0) {
+        for (int r = 0; r < b->peer_ranks; r++) bd.peer.shared[r] = b->peer_ptr[r];
+        bd.peer.cta_done = b->d_cta_done;
+        bd.peer.n_ranks = b->peer_ranks;
+        bd.peer.parity = parity;
+        bd.peer.n_words = n_cost_words;
+    }
     bcp_kernel<<<grid, db->warps_per_cta * 32, db->smem_bytes, st>>>(db->dev, bd, db->warp_bytes, db->qcap);
     b->n_kernels++;
+    if (b->peer_ranks > 0) {
+        const unsigned long long target = (unsigned long long)(b->peer_step / 2 + 1) * b->peer_ranks;
+        peer_wait_kernel<<<1, 256, 0, st>>>(b->d_peer_own, n_cost_words, parity, target, cost);
+        b->n_kernels++;
+        b->peer_step++;
+    }
     CU(cudaGetLastError());
     CU(cudaEventRecord(b->ev[3], st));
     b->propagated = true;
@@ -836,8 +857,63 @@ int pdsat_batch_models(pdsat_batch* b, int64_t* n_found, int32_t* point_of, uint
     return PDSAT_OK;
 }
 
+int pdsat_batch_peer_export(pdsat_batch* b, void* handle_out) {
+    if (!b || !handle_out) return fail(PDSAT_ERR_ARG, "pdsat_batch_peer_export: bad argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == PDSAT_IPC_HANDLE_BYTES, "IPC handle size");
+    CU(cudaSetDevice(b->db->device));
+    const size_t words = 2 * (size_t)PDSAT_COST_WORDS * b->pts.size() + 2;
+    if (!b->d_peer_own) {
+        CU(cudaMalloc(&b->d_peer_own, sizeof(unsigned long long) * words));
+        CU(cudaMemset(b->d_peer_own, 0, sizeof(unsigned long long) * words));
+        CU(cudaMalloc(&b->d_cta_done, sizeof(unsigned int)));
+        CU(cudaMemset(b->d_cta_done, 0, sizeof(unsigned int)));
+    }
+    cudaIpcMemHandle_t hd;
+    CU(cudaIpcGetMemHandle(&hd, b->d_peer_own));
+    memcpy(handle_out, &hd, sizeof(hd));
+    return PDSAT_OK;
+}
+
+int pdsat_batch_peer_connect(pdsat_batch* b, int32_t n_ranks, int32_t my_rank, const void* handles) {
+    if (!b || !handles || n_ranks < 1 || n_ranks > MAX_PEERS || my_rank < 0 || my_rank >= n_ranks)
+        return fail(PDSAT_ERR_ARG, "pdsat_batch_peer_connect: bad argument");
+    if (!b->d_peer_own) return fail(PDSAT_ERR_ARG, "pdsat_batch_peer_connect: call pdsat_batch_peer_export first");
+    CU(cudaSetDevice(b->db->device));
+    for (int r = 0; r < n_ranks; r++) {
+        if (r == my_rank) {
+            b->peer_ptr[r] = b->d_peer_own;
+            continue;
+        }
+        cudaIpcMemHandle_t hd;
+        memcpy(&hd, (const char*)handles + (size_t)r * PDSAT_IPC_HANDLE_BYTES, sizeof(hd));
+        void* p = nullptr;
+        CU(cudaIpcOpenMemHandle(&p, hd, cudaIpcMemLazyEnablePeerAccess));
+        b->peer_ptr[r] = (unsigned long long*)p;
+    }
+    b->peer_ranks = n_ranks;
+    b->peer_me = my_rank;
+    b->peer_step = 0;
+    return PDSAT_OK;
+}
+
+int pdsat_batch_peer_disconnect(pdsat_batch* b) {
+    if (!b) return fail(PDSAT_ERR_ARG, "pdsat_batch_peer_disconnect: null batch");
+    if (b->db && b->db->device >= 0) {
+        cudaSetDevice(b->db->device);
+        if (b->db->stream) cudaStreamSynchronize(b->db->stream);
+    }
+    for (int r = 0; r < b->peer_ranks; r++)
+        if (r != b->peer_me && b->peer_ptr[r]) cudaIpcCloseMemHandle(b->peer_ptr[r]);
+    for (int r = 0; r < MAX_PEERS; r++) b->peer_ptr[r] = nullptr;
+    b->peer_ranks = 0;
+    return PDSAT_OK;
+}
+
 void pdsat_batch_destroy(pdsat_batch* b) {
     if (!b) return;
+    if (b->peer_ranks) pdsat_batch_peer_disconnect(b);
+    cudaFree(b->d_peer_own);
+    cudaFree(b->d_cta_done);
     if (b->db && b->db->device >= 0) {
         cudaSetDevice(b->db->device);
         if (b->db->stream) cudaStreamSynchronize(b->db->stream);
