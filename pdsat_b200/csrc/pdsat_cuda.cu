@@ -165,7 +165,7 @@ static int sync_device_db(pdsat_db* db) {
     }
     CU(cudaSetDevice(db->device));
     free_device_db(db);
-    const int max_smem = 227 * 1024;
+    const int max_smem = 227 * 1024 - 64;  // the kernel also has a few bytes of static shared memory
     // occurrence offsets get one shared-memory copy per CTA if that costs at most one warp
     const int occ_off_bytes = ((n_lit + 1) * 4 + 15) & ~15;
     int wpc = max_smem / warp_bytes;
