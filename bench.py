@@ -247,7 +247,7 @@ def run_ours(args):
     reduce_mode = "none"
     if dist is not None:
         reduce_mode = "nccl"
-        if args.reduce == "peer":
+        if args.reduce in ("peer", "auto"):
             try:
                 mine = torch.frombuffer(bytearray(batch.peer_export()), dtype=torch.uint8).cuda()
                 allh = [torch.empty(64, dtype=torch.uint8, device="cuda") for _ in range(world)]
@@ -493,8 +493,9 @@ def main():
     ap.add_argument("--cpu-samples", type=int, default=1500, help="CPU-arm samples per core per step")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the secondary workloads")
-    ap.add_argument("--reduce", default="peer", choices=["peer", "nccl"],
-                    help="N > 1: fused NVLink peer-memory reduce (default) or NCCL all-reduce")
+    ap.add_argument("--reduce", default="auto", choices=["auto", "peer", "nccl"],
+                    help="N > 1: fused NVLink peer-memory reduce (auto/peer; falls back to NCCL if CUDA IPC "
+                         "is unavailable) or the separate NCCL all-reduce (DESIGN.md section 6)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

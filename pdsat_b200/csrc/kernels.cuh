@@ -62,6 +62,7 @@ struct PeerDev {
     unsigned long long* shared[MAX_PEERS];  // rank r's buffer as mapped in this process
     unsigned int* cta_done;                 // local ticket counter (last-CTA detection)
     int32_t n_ranks;
+    int32_t me;
     int32_t parity;
     int32_t n_words;                        // accumulators per parity = n_points * 8
 };
@@ -831,17 +832,19 @@ bcp_kernel(DbDev db, BatchDev b, int warp_bytes, int qcap) {
         __syncthreads();
         if (s_ticket == gridDim.x - 1) {
             __threadfence();
-            const int nw = b.peer.n_words;
-            for (int i = threadIdx.x; i < nw; i += blockDim.x) {
+            const int nw = b.peer.n_words, nr = b.peer.n_ranks;
+            // one fire-and-forget reduction per (word, rank); each rank starts with a different
+            // target so that the ranks do not all hit the same peer at the same moment
+            for (int j = threadIdx.x; j < nw * nr; j += blockDim.x) {
+                const int i = j % nw;
+                const int r = (j / nw + b.peer.me) % nr;
                 const unsigned long long v = __ldcg(&b.cost[i]);
-                if (v)
-                    for (int r = 0; r < b.peer.n_ranks; r++)
-                        atomicAdd_system(&b.peer.shared[r][(size_t)b.peer.parity * nw + i], v);
+                if (v) atomicAdd_system(&b.peer.shared[r][(size_t)b.peer.parity * nw + i], v);
             }
             __threadfence_system();
             __syncthreads();
-            if (threadIdx.x < b.peer.n_ranks)
-                atomicAdd_system(&b.peer.shared[threadIdx.x][(size_t)2 * nw + b.peer.parity], 1ull);
+            if (threadIdx.x < nr)
+                atomicAdd_system(&b.peer.shared[(threadIdx.x + b.peer.me) % nr][(size_t)2 * nw + b.peer.parity], 1ull);
             if (threadIdx.x == 0) *b.peer.cta_done = 0;
         }
     }
@@ -853,7 +856,7 @@ __global__ void peer_wait_kernel(unsigned long long* shared, int n_words, int pa
                                  unsigned long long* cost_out) {
     volatile unsigned long long* done = shared + (size_t)2 * n_words + parity;
     if (threadIdx.x == 0) {
-        while (*done < target) __nanosleep(200);
+        while (*done < target) __nanosleep(50);
         __threadfence_system();
     }
     __syncthreads();

@@ -714,6 +714,7 @@ int pdsat_batch_propagate(pdsat_batch* b) {
         for (int r = 0; r < b->peer_ranks; r++) bd.peer.shared[r] = b->peer_ptr[r];
         bd.peer.cta_done = b->d_cta_done;
         bd.peer.n_ranks = b->peer_ranks;
+        bd.peer.me = b->peer_me;
         bd.peer.parity = parity;
         bd.peer.n_words = n_cost_words;
     }
