@@ -597,19 +597,45 @@ bcp_kernel(DbDev db, BatchDev b, int warp_bytes, int qcap) {
     acc.point = -1;
 
     const uint64_t stride = (uint64_t)gridDim.x * wpc;
+    // current point, cached in registers (a warp usually stays inside one point for many groups)
+    int p = -1;
+    uint64_t P_start = 0, P_end = 0, P_word_off = 0, P_n_samples = 0;
+    uint32_t k = 0, P_var_off = 0, P_n_assumed = 0, P_cand_off = 0, P_cand_cnt = 0, P_code0 = 0;
+    // software prefetch: the word of set position `lane` of the NEXT group is requested while
+    // the current group is processed (the per-group critical path is this HBM load)
+    uint64_t pf_bits = 0;
+    bool pf_valid = false;
     for (uint64_t g = (uint64_t)blockIdx.x * wpc + warp; g < b.n_groups; g += stride) {
-        const int p = find_point(b.points, b.n_points, g);
-        if (p != acc.point) {
+        if (p < 0 || g >= P_end) {
+            p = find_point(b.points, b.n_points, g);
+            const PointDev* pt = &b.points[p];
+            P_start = pt->group_start;
+            P_end = p + 1 < b.n_points ? b.points[p + 1].group_start : b.n_groups;
+            P_word_off = pt->word_off;
+            P_n_samples = pt->n_samples;
+            k = pt->k;
+            P_var_off = pt->var_off;
+            P_n_assumed = pt->n_assumed_live;
+            P_cand_off = pt->cand_off;
+            P_cand_cnt = pt->cand_cnt;
+            P_code0 = lane < (int)k ? b.setcode[P_var_off + lane] : 0u;
+            pf_valid = false;
             flush_acc(acc, b.cost, lane);
             acc.point = p;
         }
-        const PointDev* pt = &b.points[p];
-        const uint64_t gi = g - pt->group_start;
+        const uint64_t gi = g - P_start;
         const uint64_t s0 = gi * 64;
-        const uint64_t left = pt->n_samples - s0;
+        const uint64_t left = P_n_samples - s0;
         const uint64_t valid = left >= 64 ? ~0ull : ((1ull << left) - 1);
-        const uint32_t k = pt->k;
-        const uint32_t* code = b.setcode + pt->var_off;
+        const uint32_t* code = b.setcode + P_var_off;
+        const uint64_t* w = b.words + P_word_off + gi * k;
+        uint64_t bits0 = pf_bits;
+        if (!pf_valid && lane < (int)k) bits0 = w[lane];
+        {
+            const uint64_t gn = g + stride;
+            pf_valid = gn < P_end;
+            if (pf_valid && lane < (int)k) pf_bits = b.words[P_word_off + (gn - P_start) * k + lane];
+        }
 
         if (lane == 0) {
             *c.dead = db.unsat ? valid : 0;
@@ -620,10 +646,9 @@ bcp_kernel(DbDev db, BatchDev b, int warp_bytes, int qcap) {
 
         // ---- (1) assumptions (src_mpi/mpi_predicter.cpp:3236-3242: true bit => positive literal)
         if (!db.unsat) {
-            const uint64_t* w = b.words + pt->word_off + gi * k;
             for (uint32_t j = lane; j < k; j += 32) {
-                const uint32_t cd = code[j];
-                const uint64_t bits = w[j];
+                const uint32_t cd = j < 32 ? P_code0 : code[j];
+                const uint64_t bits = j < 32 ? bits0 : w[j];
                 if (cd & SETCODE_FIXED) {
                     // variable already assigned at level 0: a contradicting value is a
                     // conflict (addClause_ drops the false literal: empty clause)
@@ -637,9 +662,9 @@ bcp_kernel(DbDev db, BatchDev b, int warp_bytes, int qcap) {
             __syncwarp();
 
             // ---- (2) first wave over the point's candidate clauses
-            if (pt->cand_cnt) {
+            if (P_cand_cnt) {
                 const uint64_t live = valid & ~*(volatile uint64_t*)c.dead;
-                visit_records(db.rec, b.cand + pt->cand_off, pt->cand_cnt, c, live, lane);
+                visit_records(db.rec, b.cand + P_cand_off, P_cand_cnt, c, live, lane);
                 __syncwarp();
             }
 
@@ -707,7 +732,7 @@ bcp_kernel(DbDev db, BatchDev b, int warp_bytes, int qcap) {
         acc.touched += n_touched;
         uint32_t cnt0, cnt1;  // assigned live variables of samples lane, lane+32
         if (n_touched == 0) {
-            cnt0 = cnt1 = pt->n_assumed_live;
+            cnt0 = cnt1 = P_n_assumed;
         } else {
             // bit-sliced population count over the implied planes: per sample, how many
             // literals of the undo list are set (each implied variable has one polarity per
@@ -743,8 +768,8 @@ bcp_kernel(DbDev db, BatchDev b, int warp_bytes, int qcap) {
                 cnt0 |= (uint32_t)((t >> lane) & 1ull) << q;
                 cnt1 |= (uint32_t)((t >> (lane + 32)) & 1ull) << q;
             }
-            cnt0 += pt->n_assumed_live;
-            cnt1 += pt->n_assumed_live;
+            cnt0 += P_n_assumed;
+            cnt1 += P_n_assumed;
         }
         const bool ok0 = (okm >> lane) & 1ull, ok1 = (okm >> (lane + 32)) & 1ull;
         const uint32_t full_lo = __ballot_sync(0xffffffffu, ok0 && cnt0 == (uint32_t)db.n_live);
@@ -758,7 +783,7 @@ bcp_kernel(DbDev db, BatchDev b, int warp_bytes, int qcap) {
         } else {
             uint32_t lsum = (ok0 ? t0 : 0) + (ok1 ? t1 : 0);
             uint32_t lsq = (ok0 ? t0 * t0 : 0) + (ok1 ? t1 * t1 : 0);
-            uint32_t limp = (ok0 && cnt0 > pt->n_assumed_live ? 1 : 0) + (ok1 && cnt1 > pt->n_assumed_live ? 1 : 0);
+            uint32_t limp = (ok0 && cnt0 > P_n_assumed ? 1 : 0) + (ok1 && cnt1 > P_n_assumed ? 1 : 0);
             acc.sum += __reduce_add_sync(0xffffffffu, lsum);
             acc.sumsq += __reduce_add_sync(0xffffffffu, lsq);
             acc.n_impl += __reduce_add_sync(0xffffffffu, limp);
@@ -807,7 +832,7 @@ bcp_kernel(DbDev db, BatchDev b, int warp_bytes, int qcap) {
         // ---- (5) undo: clear the assumption planes, the implied planes and the queue flags
         if (!db.unsat) {
             for (uint32_t j = lane; j < k; j += 32) {
-                const uint32_t cd = code[j];
+                const uint32_t cd = j < 32 ? P_code0 : code[j];
                 if (!(cd & SETCODE_FIXED)) {
                     c.S[cd] = 0;
                     c.S[cd ^ 1] = 0;
