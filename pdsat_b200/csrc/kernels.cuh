@@ -397,11 +397,23 @@ struct WarpCtx {
     uint16_t* queue;
     uint16_t* touched;
     uint32_t* inq;
+    uint32_t* tset;     // bitset "literal is in the undo log"
     uint64_t* dead;     // samples in conflict
     uint32_t* qtail;
     uint32_t* ntouched;
     uint32_t qmask;
 };
+
+// 64-bit OR into shared memory as two native 32-bit ATOMS.OR (a 64-bit shared atomicOr
+// compiles to a compare-and-swap spin loop); returns the previous value of the halves touched
+__device__ __forceinline__ uint64_t or64_shared(uint64_t* p, uint64_t v) {
+    uint32_t* q = reinterpret_cast<uint32_t*>(p);
+    const uint32_t lo = (uint32_t)v, hi = (uint32_t)(v >> 32);
+    uint32_t olo = 0, ohi = 0;
+    if (lo) olo = atomicOr(q, lo);
+    if (hi) ohi = atomicOr(q + 1, hi);
+    return ((uint64_t)ohi << 32) | olo;
+}
 
 __device__ __forceinline__ void push_lit(const WarpCtx& c, uint32_t l) {
     const uint32_t bit = 1u << (l & 31);
@@ -461,9 +473,14 @@ __device__ __forceinline__ void eval_rec(const uint4& r, const uint4* __restrict
 __device__ __forceinline__ void imply_lit(const WarpCtx& c, uint32_t m, uint64_t imp) {
     imp &= ~c.S[m ^ 1];
     if (imp) {
-        const uint64_t old = atomicOr((unsigned long long*)&c.S[m ^ 1], (unsigned long long)imp);
-        if (old == 0) c.touched[atomicAdd(c.ntouched, 1u)] = (uint16_t)(m ^ 1);
-        if (imp & ~old) push_lit(c, m ^ 1);
+        const uint32_t l = m ^ 1;
+        const uint64_t old = or64_shared(&c.S[l], imp);
+        if (imp & ~old) {
+            // first time this literal is implied in the group: log it once (undo list)
+            const uint32_t bit = 1u << (l & 31);
+            if (!(atomicOr(&c.tset[l >> 5], bit) & bit)) c.touched[atomicAdd(c.ntouched, 1u)] = (uint16_t)l;
+            push_lit(c, l);
+        }
     }
 }
 
@@ -498,7 +515,7 @@ __device__ __forceinline__ void settle_rec(const uint4& r, const uint4* __restri
                                            uint64_t live, uint64_t ge1, uint64_t ge2) {
     const uint64_t confl = ~ge1 & live;
     const uint64_t unit = ge1 & ~ge2 & live;
-    if (confl) atomicOr((unsigned long long*)c.dead, (unsigned long long)confl);
+    if (confl) or64_shared(c.dead, confl);
     if (unit) imply_from_rec(r, rec, c, unit);
 }
 
@@ -572,7 +589,8 @@ bcp_kernel(DbDev db, BatchDev b, int warp_bytes, int qcap) {
     c.touched = c.queue + qcap;                 // qcap (a power of two) ring slots
     c.inq = (uint32_t*)(c.touched + ((db.n_lit + 2 + 3) & ~3));
     const int inq_words = (db.n_lit + 31) >> 5;
-    c.dead = (uint64_t*)(c.inq + ((inq_words + 1) & ~1));
+    c.tset = c.inq + ((inq_words + 1) & ~1);
+    c.dead = (uint64_t*)(c.tset + ((inq_words + 1) & ~1));
     c.qtail = (uint32_t*)(c.dead + 1);
     c.ntouched = c.qtail + 1;
     c.qmask = (uint32_t)qcap - 1;
@@ -589,7 +607,10 @@ bcp_kernel(DbDev db, BatchDev b, int warp_bytes, int qcap) {
 
     // the planes start clean and every group cleans up after itself
     for (int i = lane; i < n_planes; i += 32) c.S[i] = i == db.n_lit ? ~0ull : 0ull;  // plane n_lit = pad
-    for (int i = lane; i < inq_words; i += 32) c.inq[i] = 0;
+    for (int i = lane; i < inq_words; i += 32) {
+        c.inq[i] = 0;
+        c.tset[i] = 0;
+    }
     __syncwarp();
 
     WarpAcc acc;
@@ -653,7 +674,7 @@ bcp_kernel(DbDev db, BatchDev b, int warp_bytes, int qcap) {
                     // variable already assigned at level 0: a contradicting value is a
                     // conflict (addClause_ drops the false literal: empty clause)
                     const uint64_t bad = ((cd & 1u) ? bits : ~bits) & valid;
-                    if (bad) atomicOr((unsigned long long*)c.dead, (unsigned long long)bad);
+                    if (bad) or64_shared(c.dead, bad);
                 } else {
                     c.S[cd] = bits & valid;
                     c.S[cd ^ 1] = ~bits & valid;
@@ -842,6 +863,7 @@ bcp_kernel(DbDev db, BatchDev b, int warp_bytes, int qcap) {
                 const uint32_t l = c.touched[i];
                 c.S[l] = 0;
                 atomicAnd(&c.inq[l >> 5], ~(1u << (l & 31)));
+                atomicAnd(&c.tset[l >> 5], ~(1u << (l & 31)));
             }
         }
         __syncwarp();

@@ -155,7 +155,7 @@ static int sync_device_db(pdsat_db* db) {
     int qcap = 4;  // queue ring (power of two >= one slot per literal)
     while (qcap < n_lit + 2) qcap <<= 1;
     int inq_words = (n_lit + 31) / 32;
-    int warp_bytes = n_planes * 8 + qcap * 2 + ((n_lit + 2 + 3) & ~3) * 2 + ((inq_words + 1) & ~1) * 4 + 16;
+    int warp_bytes = n_planes * 8 + qcap * 2 + ((n_lit + 2 + 3) & ~3) * 2 + 2 * ((inq_words + 1) & ~1) * 4 + 16;
     warp_bytes = (warp_bytes + 15) & ~15;
     db->qcap = qcap;
     db->warp_bytes = warp_bytes;
