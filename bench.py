@@ -476,6 +476,8 @@ def run_ours(args):
             cb.pop("wall_s", None)
             line["cpu_baseline"] = cb
         print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()  # nobody frees a peer-mapped buffer while another rank may still use it
     batch.close()
     db.close()
     if dist is not None:
