@@ -322,6 +322,7 @@ def run_ours(args):
     e2e_s = time.perf_counter() - t0
     n_reduced_check = c.n
     fill_ms_last, _ = batch.last_ms()
+    h2d_per_step = batch.h2d_bytes()
     # the timed regions above last milliseconds; keep the same fill+propagate load running for
     # ~1.5 s more so that nvidia-smi (100 ms period) sees the clocks under this load
     t_probe = time.perf_counter()
@@ -448,7 +449,9 @@ def run_ours(args):
             "config": workload_config(n),
             "propagated_literals_per_s": value * (info.n_base_assigned + len(SET_VARS)),
             "e2e": {"value": e2e_value, "unit": "samples/s",
-                    "h2d_bytes_per_step": 624 * 4 + 16 + 88, "d2h_bytes_per_step": 8 * api.COST_WORDS},
+                    "h2d_bytes_per_step": int(h2d_per_step), "d2h_bytes_per_step": 8 * api.COST_WORDS,
+                    "note": "inputs are descriptors (set, seed, window): sample values are generated on the "
+                            "device; H2D = point descriptors + generator seed state + jump plan"},
             "gpu_launches": int(gpu_launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,

@@ -154,6 +154,9 @@ int pdsat_batch_sync(pdsat_batch* b);
 /* device time of the last fill / propagate on this batch, CUDA events on the launch stream */
 int pdsat_batch_last_ms(pdsat_batch* b, float* fill_ms, float* propagate_ms);
 int pdsat_batch_launch_count(pdsat_batch* b, int64_t* n_kernels);
+/* host->device bytes copied by the last pdsat_batch_fill (descriptors, generator seeds, jump plan,
+ * explicit values) */
+int pdsat_batch_h2d_bytes(pdsat_batch* b, int64_t* bytes);
 
 /* ---- cost reduce -------------------------------------------------------------------------
  * Replaces the per-sample MPI replies (mpi_predicter.cpp:3266-3270) and their storage

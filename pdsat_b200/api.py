@@ -29,7 +29,7 @@ EXPORTS = [
     "pdsat_batch_set_cost_buffer", "pdsat_batch_costs", "pdsat_batch_flags", "pdsat_batch_trail",
     "pdsat_batch_assign", "pdsat_batch_models", "pdsat_batch_destroy", "pdsat_eval_batch",
     "pdsat_mt19937_bool_rand", "pdsat_batch_peer_export", "pdsat_batch_peer_connect",
-    "pdsat_batch_peer_disconnect",
+    "pdsat_batch_peer_disconnect", "pdsat_batch_h2d_bytes",
 ]
 
 
@@ -100,6 +100,7 @@ def lib():
     L.pdsat_batch_peer_export.argtypes = [C.c_void_p, C.c_void_p]
     L.pdsat_batch_peer_connect.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
     L.pdsat_batch_peer_disconnect.argtypes = [C.c_void_p]
+    L.pdsat_batch_h2d_bytes.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
     _lib = L
     return L
 
@@ -255,6 +256,11 @@ class Batch:
     def launch_count(self) -> int:
         n = C.c_int64(0)
         _check(lib().pdsat_batch_launch_count(self.h, C.byref(n)))
+        return n.value
+
+    def h2d_bytes(self) -> int:
+        n = C.c_int64(0)
+        _check(lib().pdsat_batch_h2d_bytes(self.h, C.byref(n)))
         return n.value
 
     def cost_device_ptr(self) -> int:

@@ -29,7 +29,6 @@ struct DbDev {
     int32_t n_lit;            // 2*n_live
     int32_t n_base_assigned;
     int32_t unsat;            // level-0 conflict: every sample is a conflict
-    int32_t count_bits;       // bits needed to count to n_live
 };
 
 struct PointDev {

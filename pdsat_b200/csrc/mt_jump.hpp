@@ -33,13 +33,6 @@ inline void mt19937_twist(uint32_t* mt) {
     }
 }
 
-// state BEFORE the twist that yields draws 624*round .. 624*round+623 (sequential; tests
-// and small offsets only)
-inline void mt19937_state_at_round(uint32_t seed, uint64_t round, uint32_t* out) {
-    mt19937_seed(seed, out);
-    for (uint64_t r = 0; r < round; r++) mt19937_twist(out);
-}
-
 class MtJumpPolys {
 public:
     static constexpr int DEG = 19937;

@@ -69,7 +69,7 @@ struct pdsat_batch {
     uint32_t out_flags = 0;
     int32_t max_models = 0;
     int32_t model_words = 0;
-    uint64_t n_groups = 0, n_words = 0, n_stream_words = 0;
+    uint64_t n_groups = 0, n_words = 0;
     // device
     PointDev* d_points = nullptr;
     uint32_t* d_setcode = nullptr;
@@ -111,6 +111,7 @@ struct pdsat_batch {
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     bool filled = false, propagated = false;
     int64_t n_kernels = 0;
+    int64_t h2d_bytes_last_fill = 0;
 };
 
 extern "C" {
@@ -197,7 +198,6 @@ static int sync_device_db(pdsat_db* db) {
     db->dev.n_lit = n_lit;
     db->dev.n_base_assigned = h.n_base_assigned;
     db->dev.unsat = h.base_ok ? 0 : 1;
-    db->dev.count_bits = count_bits_for(h.n_live);
     CU(cudaFuncSetAttribute(bcp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     return PDSAT_OK;
 }
@@ -443,7 +443,6 @@ int pdsat_batch_create(pdsat_db* db, int32_t n_points, const pdsat_point* points
     }
     b->n_groups = groups;
     b->n_words = words;
-    b->n_stream_words = stream_words;
 
     auto bail = [&](int code, const std::string& m) {
         pdsat_batch_destroy(b);
@@ -574,6 +573,7 @@ int pdsat_batch_fill(pdsat_batch* b) {
     cudaStream_t st = db->stream;
     CU(cudaEventRecord(b->ev[0], st));
     CU(cudaMemcpyAsync(b->d_points, b->h_points, sizeof(PointDev) * b->pts.size(), cudaMemcpyHostToDevice, st));
+    int64_t h2d = (int64_t)(sizeof(PointDev) * b->pts.size());
     if (b->n_mt_segs) {
         // seed states -> part 0 of slot 2p (other parts zero); jump-ahead (mt_jump.hpp) places
         // every other segment
@@ -585,6 +585,7 @@ int pdsat_batch_fill(pdsat_batch* b) {
         CU(cudaMemsetAsync(b->d_mt_states, 0, sizeof(uint32_t) * 624 * MT_PARTS * 2 * b->n_mt_points, st));
         CU(cudaMemcpy2DAsync(b->d_mt_states, sizeof(uint32_t) * 624 * MT_PARTS * 2, b->h_mt_states, sizeof(uint32_t) * 624,
                              sizeof(uint32_t) * 624, b->n_mt_points, cudaMemcpyHostToDevice, st));
+        h2d += (int64_t)(sizeof(uint32_t) * 624 * b->n_mt_points + sizeof(MtSegment) * b->n_mt_segs);
         // launch plan: (a) per set bit t of the first round, a jump by 2^t rounds between the
         // point's two slots; (b) binary tree over the segments, top level first
         struct Launch { size_t off, cnt; };
@@ -641,6 +642,7 @@ int pdsat_batch_fill(pdsat_batch* b) {
                 db->n_polys++;
             }
             CU(cudaMemcpyAsync(b->d_mt_tasks, b->h_mt_tasks, sizeof(MtJumpTask) * nt, cudaMemcpyHostToDevice, st));
+            h2d += (int64_t)(sizeof(MtJumpTask) * nt);
             for (auto& L : launches) {
                 mt19937_jump_kernel<<<(unsigned)L.cnt * MT_PARTS, MT_JUMP_THREADS, MT_JUMP_SMEM, st>>>(db->d_polys, b->d_mt_states,
                                                                                              b->d_mt_tasks + L.off);
@@ -656,6 +658,7 @@ int pdsat_batch_fill(pdsat_batch* b) {
             if (hp.mode != PDSAT_MODE_EXPLICIT) continue;
             CU(cudaMemcpyAsync(b->d_stream + hp.stream_off, b->h_stream + hp.stream_off,
                                sizeof(uint32_t) * hp.stream_words, cudaMemcpyHostToDevice, st));
+            h2d += (int64_t)(sizeof(uint32_t) * hp.stream_words);
         }
     }
     BatchDev bd{};
@@ -672,6 +675,7 @@ int pdsat_batch_fill(pdsat_batch* b) {
     CU(cudaGetLastError());
     CU(cudaEventRecord(b->ev[1], st));
     b->filled = true;
+    b->h2d_bytes_last_fill = h2d;
     return PDSAT_OK;
 }
 
@@ -755,6 +759,12 @@ int pdsat_batch_last_ms(pdsat_batch* b, float* fill_ms, float* propagate_ms) {
 int pdsat_batch_launch_count(pdsat_batch* b, int64_t* n_kernels) {
     if (!b || !n_kernels) return fail(PDSAT_ERR_ARG, "pdsat_batch_launch_count: bad argument");
     *n_kernels = b->n_kernels;
+    return PDSAT_OK;
+}
+
+int pdsat_batch_h2d_bytes(pdsat_batch* b, int64_t* bytes) {
+    if (!b || !bytes) return fail(PDSAT_ERR_ARG, "pdsat_batch_h2d_bytes: bad argument");
+    *bytes = b->h2d_bytes_last_fill;
     return PDSAT_OK;
 }
 

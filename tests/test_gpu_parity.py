@@ -362,3 +362,25 @@ def test_gpu_enumeration_vs_reference_cube(case, bivium, golden, cuda_lib):
     assert len(rc2) == rc2_valid and survivors <= rc2
     if case in ("n161_k16", "n100_k14", "n60_k12", "n150_k10"):
         assert survivors == rc2
+
+
+def test_gpu_everything_fixed_at_level0(oracle_mod, cuda_lib):
+    """No live variable at all: set variables are all level-0 fixed; a matching assignment is a
+    (trivially) full model, a contradicting one a conflict."""
+    from pdsat_b200 import api, fixtures as fx
+    clauses = [[1], [2], [-1, 3]]
+    offs, lits = fx.to_csr(clauses)
+    db = api.ClauseDb(3, offs, lits, device=0)
+    assert db.info().n_live_vars == 0 and db.info().status == api.PDSAT_OK
+    P = oracle_mod.Oracle(3, offs, lits, "port")
+    b = api.Batch(db, [api.Point([1, 3], 4, api.MODE_ENUM), api.Point([2], 1, api.MODE_ENUM, first_sample=1)],
+                  api.OUT_FLAGS | api.OUT_TRAIL, max_models=8)
+    costs = b.run()
+    conflict, full = b.flags(0)
+    for s in range(4):
+        r, _ = P.bcp(list(oracle_mod.enum_assumptions([1, 3], s)))
+        assert bool(conflict[s]) == bool(r.conflict) and bool(full[s]) == bool(r.full)
+    assert (costs[0].n_conflict, costs[0].n_full, costs[0].sum_trail) == (3, 1, 3)
+    assert (costs[1].n, costs[1].n_conflict, costs[1].n_full) == (1, 0, 1)
+    found, _, _, models = b.models()
+    assert found == 2 and all(list(m) == [1, 1, 1] for m in models)
