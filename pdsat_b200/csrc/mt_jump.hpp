@@ -16,6 +16,7 @@
 #pragma once
 #include <cstdint>
 #include <cstring>
+#include <map>
 #include <mutex>
 #include <vector>
 
@@ -64,6 +65,26 @@ public:
         return dev_format_[t].data();
     }
 
+    // x^(624 * rounds) mod phi for an arbitrary round count: product of the chain polynomials
+    // of the set bits (one modular multiplication each, a few ms); cached per round count
+    const uint32_t* poly_for_rounds(uint64_t rounds) {
+        int top = 63;
+        while (top > 0 && !((rounds >> top) & 1ull)) top--;
+        poly(top);  // make sure the chain is long enough (takes and releases the lock)
+        std::lock_guard<std::mutex> lk(mu_);
+        auto it = composite_.find(rounds);
+        if (it != composite_.end()) return it->second.data();
+        std::vector<uint64_t> acc;
+        for (int t = 0; t <= top; t++) {
+            if (!((rounds >> t) & 1ull)) continue;
+            if (acc.empty()) acc = chain_[t];
+            else acc = mul_mod(acc, chain_[t]);
+        }
+        std::vector<uint32_t> d(POLY_WORDS32, 0);
+        for (int i = 0; i < POLY_WORDS32; i++) d[i] = (uint32_t)(acc[i >> 1] >> ((i & 1) * 32));
+        return composite_.emplace(rounds, std::move(d)).first->second.data();
+    }
+
     int degree_of_phi() {
         std::lock_guard<std::mutex> lk(mu_);
         ensure_phi();
@@ -77,6 +98,7 @@ private:
     std::vector<std::vector<uint64_t>> phi_shift_;  // phi << s for s = 0..63 (W64 + 1 words)
     std::vector<std::vector<uint64_t>> chain_;
     std::vector<std::vector<uint32_t>> dev_format_;
+    std::map<uint64_t, std::vector<uint32_t>> composite_;
 
     // Berlekamp-Massey over GF(2) on one output bit of the generator: the minimal polynomial
     // of that bit sequence is the characteristic polynomial (it is primitive of degree 19937).
@@ -170,6 +192,28 @@ private:
             sq[2 * w] = spread((uint32_t)p[w]);
             sq[2 * w + 1] = spread((uint32_t)(p[w] >> 32));
         }
+        return reduce(sq);
+    }
+
+    // a(x) * b(x) mod phi (both already reduced): shift-and-xor product, then reduction
+    std::vector<uint64_t> mul_mod(const std::vector<uint64_t>& a, const std::vector<uint64_t>& b) {
+        const int W2 = 2 * W64 + 4;
+        std::vector<uint64_t> pr(W2, 0);
+        for (int i = 0; i < DEG; i++) {
+            if (!((a[i >> 6] >> (i & 63)) & 1ull)) continue;
+            const int sw = i >> 6, sh = i & 63;
+            for (int w = 0; w < W64; w++) {
+                const uint64_t v = b[w];
+                if (!v) continue;
+                pr[sw + w] ^= v << sh;
+                if (sh) pr[sw + w + 1] ^= v >> (64 - sh);
+            }
+        }
+        return reduce(pr);
+    }
+
+    // reduce a polynomial of degree < 2*DEG modulo phi, from the top bit down
+    std::vector<uint64_t> reduce(std::vector<uint64_t>& sq) {
         for (int i = 2 * (DEG - 1); i >= DEG; i--) {
             if (!((sq[i >> 6] >> (i & 63)) & 1ull)) continue;
             const int sh = i - DEG;  // xor phi << sh

@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -43,8 +44,12 @@ struct pdsat_db {
     // mt19937 jump polynomials x^(624*2^t) mod phi resident on the device (lazy)
     uint32_t* d_polys = nullptr;
     int n_polys = 0;
+    // composite polynomials x^(624*R0) for stream offsets that keep coming back (a rank's
+    // shard offset): slot MAX_POLYS + i of d_polys
+    std::map<uint64_t, int> comp_slot, comp_seen;
 };
 static constexpr int MAX_POLYS = 64;
+static constexpr int MAX_COMP_POLYS = 64;
 
 struct HostPoint {
     std::vector<int32_t> set_vars;
@@ -593,11 +598,36 @@ int pdsat_batch_fill(pdsat_batch* b) {
         size_t nt = 0;
         std::vector<uint32_t> cur_slot(b->pts.size());
         for (size_t p = 0; p < b->pts.size(); p++) cur_slot[p] = 2 * b->pts[p].mt_index;
+        // an offset seen for the second time gets ONE jump with the composite polynomial
+        // x^(624*R0) (built on the host once, ~0.1 s) instead of one jump per set bit
+        if (!db->d_polys) CU(cudaMalloc(&db->d_polys, sizeof(uint32_t) * 624 * (MAX_POLYS + MAX_COMP_POLYS)));
+        std::vector<char> use_comp(b->pts.size(), 0);
+        {
+            size_t start = nt;
+            for (size_t p = 0; p < b->pts.size(); p++) {
+                HostPoint& hp = b->pts[p];
+                const uint64_t r0 = hp.mt_first_round;
+                if (hp.mode != PDSAT_MODE_RANDOM_MT19937 || __builtin_popcountll(r0) < 2) continue;
+                auto it = db->comp_slot.find(r0);
+                if (it == db->comp_slot.end()) {
+                    if (++db->comp_seen[r0] < 2 || (int)db->comp_slot.size() >= MAX_COMP_POLYS) continue;
+                    const int slot = MAX_POLYS + (int)db->comp_slot.size();
+                    CU(cudaMemcpyAsync(db->d_polys + (size_t)slot * 624, MtJumpPolys::instance().poly_for_rounds(r0),
+                                       sizeof(uint32_t) * 624, cudaMemcpyHostToDevice, st));
+                    it = db->comp_slot.emplace(r0, slot).first;
+                }
+                const uint32_t other = cur_slot[p] ^ 1u;
+                b->h_mt_tasks[nt++] = MtJumpTask{cur_slot[p], other, (uint32_t)it->second, 0};
+                cur_slot[p] = other;
+                use_comp[p] = 1;
+            }
+            if (nt > start) launches.push_back({start, nt - start});
+        }
         for (int t = 0; t < 64; t++) {
             size_t start = nt;
             for (size_t p = 0; p < b->pts.size(); p++) {
                 HostPoint& hp = b->pts[p];
-                if (hp.mode != PDSAT_MODE_RANDOM_MT19937 || !((hp.mt_first_round >> t) & 1ull)) continue;
+                if (hp.mode != PDSAT_MODE_RANDOM_MT19937 || use_comp[p] || !((hp.mt_first_round >> t) & 1ull)) continue;
                 const uint32_t other = cur_slot[p] ^ 1u;
                 b->h_mt_tasks[nt++] = MtJumpTask{cur_slot[p], other, (uint32_t)t, 0};
                 cur_slot[p] = other;
@@ -633,8 +663,7 @@ int pdsat_batch_fill(pdsat_batch* b) {
             }
         }
         if (max_poly >= MAX_POLYS) return fail(PDSAT_ERR_LIMIT, "mt19937 stream offset too large");
-        if (max_poly >= 0) {
-            if (!db->d_polys) CU(cudaMalloc(&db->d_polys, sizeof(uint32_t) * 624 * MAX_POLYS));
+        if (!launches.empty()) {
             while (db->n_polys <= max_poly) {
                 const uint32_t* pl = MtJumpPolys::instance().poly(db->n_polys);
                 CU(cudaMemcpyAsync(db->d_polys + (size_t)db->n_polys * 624, pl, sizeof(uint32_t) * 624,

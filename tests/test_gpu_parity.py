@@ -279,6 +279,17 @@ def test_gpu_mt19937_multi_segment_batch(bivium, golden, oracle_mod, cuda_lib):
     for s in range(10):
         for j, v in enumerate(sv):
             assert asg[s][v - 1] == (A[s][j] & 1)
+    # the same offset again with other seeds: from its second appearance the offset is reached
+    # with ONE jump by the composite polynomial x^(624*R0) instead of one jump per set bit
+    for seed in (6, 7, 8):
+        b.reseed(0, seed, 777)
+        b.run()
+        for lo in (0, n - 10):
+            asg = b.assign(0, lo, 10)
+            A = oracle_mod.sample_assumptions(seed, sv, 777 + lo, 10)
+            for s in range(10):
+                for j, v in enumerate(sv):
+                    assert asg[s][v - 1] == (A[s][j] & 1), (seed, lo, s, j)
 
 
 @pytest.mark.parametrize("seed", [0, 1, 2, 3])
