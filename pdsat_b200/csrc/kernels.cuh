@@ -400,7 +400,7 @@ struct WarpCtx {
     uint64_t* dead;     // samples in conflict
     uint32_t* qtail;
     uint32_t* ntouched;
-    uint32_t qmask;
+    uint32_t qcap, qmagic;  // ring size (one slot per literal) and ceil(2^32 / qcap)
 };
 
 // 64-bit OR into shared memory as two native 32-bit ATOMS.OR (a 64-bit shared atomicOr
@@ -414,12 +414,19 @@ __device__ __forceinline__ uint64_t or64_shared(uint64_t* p, uint64_t v) {
     return ((uint64_t)ohi << 32) | olo;
 }
 
+// pos mod qcap without a division (pos stays far below 2^32)
+__device__ __forceinline__ uint32_t ring_index(const WarpCtx& c, uint32_t pos) {
+    int32_t r = (int32_t)(pos - __umulhi(pos, c.qmagic) * c.qcap);
+    if (r < 0) r += (int32_t)c.qcap;
+    return (uint32_t)r;
+}
+
 __device__ __forceinline__ void push_lit(const WarpCtx& c, uint32_t l) {
     const uint32_t bit = 1u << (l & 31);
     const uint32_t old = atomicOr(&c.inq[l >> 5], bit);
     if (!(old & bit)) {
         const uint32_t pos = atomicAdd(c.qtail, 1u);
-        c.queue[pos & c.qmask] = (uint16_t)l;
+        c.queue[ring_index(c, pos)] = (uint16_t)l;
     }
 }
 
@@ -585,14 +592,15 @@ bcp_kernel(DbDev db, BatchDev b, int warp_bytes, int qcap) {
     c.S = (uint64_t*)base;
     const int n_planes = db.n_lit + 2;
     c.queue = (uint16_t*)(c.S + n_planes);
-    c.touched = c.queue + qcap;                 // qcap (a power of two) ring slots
+    c.touched = c.queue + qcap;                 // qcap ring slots (one per literal, multiple of 4)
     c.inq = (uint32_t*)(c.touched + ((db.n_lit + 2 + 3) & ~3));
     const int inq_words = (db.n_lit + 31) >> 5;
     c.tset = c.inq + ((inq_words + 1) & ~1);
     c.dead = (uint64_t*)(c.tset + ((inq_words + 1) & ~1));
     c.qtail = (uint32_t*)(c.dead + 1);
     c.ntouched = c.qtail + 1;
-    c.qmask = (uint32_t)qcap - 1;
+    c.qcap = (uint32_t)qcap;
+    c.qmagic = (uint32_t)((0x100000000ull + (uint32_t)qcap - 1) / (uint32_t)qcap);
 
     // occurrence offsets: one copy per CTA in shared memory when it fits (saves a dependent L2
     // round trip per propagation round)
@@ -698,7 +706,7 @@ bcp_kernel(DbDev db, BatchDev b, int warp_bytes, int qcap) {
                 if (qh == qt || (deadv & valid) == valid) break;
                 const uint32_t np = min(qt - qh, (uint32_t)MULTI_POP);
                 uint32_t myl = 0, mybeg = 0, mylen = 0;
-                if (lane < (int)np) myl = c.queue[(qh + lane) & c.qmask];
+                if (lane < (int)np) myl = c.queue[ring_index(c, qh + lane)];
                 qh += np;
                 __syncwarp();
                 if (lane < (int)np) {

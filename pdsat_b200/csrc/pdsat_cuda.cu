@@ -158,8 +158,7 @@ static int sync_device_db(pdsat_db* db) {
     if (count_bits_for(h.n_live) > MAX_COUNT_BITS) return fail(PDSAT_ERR_LIMIT, "too many live variables for the counters");
     int n_lit = 2 * h.n_live;
     int n_planes = n_lit + 2;
-    int qcap = 4;  // queue ring (power of two >= one slot per literal)
-    while (qcap < n_lit + 2) qcap <<= 1;
+    int qcap = (n_lit + 2 + 3) & ~3;  // queue ring: one slot per literal
     int inq_words = (n_lit + 31) / 32;
     int warp_bytes = n_planes * 8 + qcap * 2 + ((n_lit + 2 + 3) & ~3) * 2 + 2 * ((inq_words + 1) & ~1) * 4 + 16;
     warp_bytes = (warp_bytes + 15) & ~15;
