@@ -395,3 +395,33 @@ def test_gpu_everything_fixed_at_level0(oracle_mod, cuda_lib):
     assert (costs[1].n, costs[1].n_conflict, costs[1].n_full) == (1, 0, 1)
     found, _, _, models = b.models()
     assert found == 2 and all(list(m) == [1, 1, 1] for m in models)
+
+
+@pytest.mark.parametrize("k", [30, 85])
+def test_config0_predict_estimate_matches_reference_path(k, bivium, golden, oracle_mod, cuda_lib):
+    """BASELINE.json configs[0]: 1 000-sample Monte Carlo predict of a start-state set.  The
+    reference path (fresh solver per sample, cost = Solver::propagations, GetPredict arithmetic in
+    long double) and the device path (integer sums -> host estimator) must give the same runtime
+    estimate within 1e-12 relative (north star); observed: identical."""
+    from pdsat_b200 import api, predicter as pr
+    nv, _, offs, lits = bivium
+    stream = list(golden["stream_lits"])
+    sv = pr.schema_vars("bivium_Ending2", k)
+    n = 1000
+    P = oracle_mod.Oracle(nv, offs, lits, "ref" if oracle_mod.have_ref() else "port")
+    A = oracle_mod.sample_assumptions(1, sv, 0, n)
+    cost = np.empty(n)
+    for s in range(n):
+        # eval "prep": the reference stops after BCP (Solver.cc:874-877); with "propagation" it
+        # would run the full CDCL search.  Solver::propagations is the same BCP count either way.
+        r, _ = P.predict_sample(list(A[s]) + stream, 0, want_assigns=False)
+        assert not r.conflict
+        cost[s] = float(r.propagations)
+    ref_sum, ref_med, ref_pred = oracle_mod.predict_mean(cost, k, proc_count=4)
+    db = api.ClauseDb(nv, offs, lits, device=0)
+    db.set_fixed_assumptions(stream)
+    res = pr.Predicter(db, cnf_in_set_count=n, evaluation_type="propagation", proc_count=4, base_seed=1).evaluate([sv])[0]
+    assert res.sum_cost == ref_sum
+    assert abs(float((res.predict - np.longdouble(ref_pred)) / np.longdouble(ref_pred))) <= 1e-12
+    assert abs(pr.sample_variance(res.cost) - (oracle_mod.sample_variance(cost) if cost.std() > 0 else 0.0)) <= \
+        1e-12 * max(1.0, oracle_mod.sample_variance(cost))
