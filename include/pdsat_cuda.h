@@ -39,9 +39,11 @@ enum {
 
 /* How the values of the decomposition-set variables of sample s are obtained. */
 enum {
-    /* bit j of sample s = bool_rand of draw (first_sample+s)*k + j of mt19937(seed):
-     * the reference's 1-worker order (src_mpi/mpi_predicter.cpp:3236-3242,
-     * src_common/addit_func.cpp:193-196; bool_rand == ((draw >> 31) == 0)). */
+    /* bit j of sample s = bool_rand of draw first_draw + (first_sample+s)*k + j of
+     * mt19937(seed): the reference's 1-worker order (src_mpi/mpi_predicter.cpp:3236-3242,
+     * src_common/addit_func.cpp:193-196; bool_rand == ((draw >> 31) == 0)).  first_draw is
+     * the number of draws the worker's generator has already made (it is seeded once,
+     * mpi_predicter.cpp:87, and runs on across points of different k). */
     PDSAT_MODE_RANDOM_MT19937 = 0,
     /* declared counter-based generator (NOT the reference stream): the 64 values of set
      * position j for samples [64g, 64g+64) are the bits of
@@ -67,6 +69,7 @@ typedef struct {
     uint64_t first_sample;
     uint64_t n_samples;
     const uint8_t* explicit_values;  /* EXPLICIT mode only: n_samples * k bytes        */
+    uint64_t first_draw;             /* MT19937 mode: draws already consumed (0 = fresh) */
 } pdsat_point;
 
 /* Integer-exact Monte Carlo accumulators of one point: what GetPredict needs
@@ -97,14 +100,27 @@ typedef struct {
     int32_t warps_per_cta;   /* launch shape chosen for the BCP kernel                 */
     int32_t smem_bytes;      /* dynamic shared memory per CTA                          */
     int32_t grid;            /* CTAs launched                                          */
-    int32_t db_in_smem;      /* 1 = occurrence offsets staged in shared memory (per CTA) */
+    int32_t db_in_smem;      /* 1 = index blob (occurrence offsets, gate lists, gate records)
+                                staged in shared memory by one bulk copy per CTA         */
     int32_t sm_count;
+    int32_t n_gates;         /* XOR / ANDXOR gates recognised among the live clauses     */
+    int32_t blob_bytes;      /* size of the index blob                                   */
+    int64_t n_gate_clauses;  /* live clauses replaced by gate records                    */
 } pdsat_db_info;
+
+/* One recognised gate (inspection / tests): type 0 = XOR  x[0]^...^x[m-1] = parity,
+ * type 1 = ANDXOR  x[0]^...^x[m-1] ^ (lb & lc) = parity.  x[] are 1-based variables,
+ * lb / lc MiniSat literals (2*var+sign). */
+typedef struct {
+    int32_t type, parity, m, n_clauses;
+    int32_t x[7];
+    int32_t lb, lc;
+} pdsat_gate;
 
 /* output selection for pdsat_batch_create */
 enum {
     PDSAT_OUT_FLAGS = 1,  /* per-sample conflict / full bitmaps                        */
-    PDSAT_OUT_TRAIL = 2,  /* per-sample trail size (uint16)                            */
+    PDSAT_OUT_TRAIL = 2,  /* per-sample trail size (uint32)                            */
     PDSAT_OUT_ASSIGN = 4  /* per-sample assignment of every variable (parity tests)    */
 };
 
@@ -127,14 +143,21 @@ int pdsat_upload_cnf(int device, int32_t n_vars, int64_t n_clauses, const uint32
 /* Literals assumed in EVERY sample: the keystream bits of a cipher instance
  * (src_mpi/mpi_predicter.cpp:3229-3234) or solve mode's known_dummy
  * (src_mpi/mpi_solver.cpp:199-200).  They are folded into the level-0 assignment by host
- * BCP and the device database is rebuilt; n = 0 restores the plain template. */
+ * BCP and the device database is rebuilt; n = 0 restores the plain template.
+ * The rebuild renumbers the live variables: every pdsat_batch created before this call is
+ * stale and its fill / propagate calls fail with PDSAT_ERR_ARG (destroy and re-create it). */
 int pdsat_set_fixed_assumptions(pdsat_db* db, const int32_t* lits, int32_t n);
+/* gates recognised in the current database: *n_gates = their number, at most cap are
+ * written to out (out may be NULL) */
+int pdsat_db_gates(const pdsat_db* db, int32_t cap, pdsat_gate* out, int32_t* n_gates);
 
 int pdsat_db_get_info(const pdsat_db* db, pdsat_db_info* info);
 /* level-0 assignment incl. fixed assumptions, n_vars lbool bytes */
 int pdsat_db_base_assignment(const pdsat_db* db, uint8_t* assigns);
 /* run on a caller-owned cudaStream_t (e.g. torch's current stream); NULL = own stream */
 int pdsat_set_stream(pdsat_db* db, void* cuda_stream);
+/* batches of this database that are still alive keep it alive: the memory is released when
+ * the last of them is destroyed */
 void pdsat_destroy(pdsat_db* db);
 
 /* ---- batch evaluate --------------------------------------------------------------------
@@ -146,6 +169,8 @@ int pdsat_batch_create(pdsat_db* db, int32_t n_points, const pdsat_point* points
                        int32_t max_models, pdsat_batch** out);
 /* change the stream position of a point without reallocating (RANDOM / ENUM modes) */
 int pdsat_batch_reseed(pdsat_batch* b, int32_t point, uint64_t seed, uint64_t first_sample);
+/* move a MT19937 point along its worker's stream (see pdsat_point.first_draw) */
+int pdsat_batch_set_first_draw(pdsat_batch* b, int32_t point, uint64_t first_draw);
 /* stage 1 (async): sample values -> bit-sliced assumption words in HBM */
 int pdsat_batch_fill(pdsat_batch* b);
 /* stage 2 (async): BCP of every sample + per-point cost accumulation */
@@ -182,7 +207,7 @@ int pdsat_batch_peer_disconnect(pdsat_batch* b);
 /* ---- per-sample results (optional outputs) ------------------------------------------- */
 /* bit s%64 of word s/64 (s counted inside the point) */
 int pdsat_batch_flags(pdsat_batch* b, int32_t point, uint64_t* conflict_bits, uint64_t* full_bits);
-int pdsat_batch_trail(pdsat_batch* b, int32_t point, uint16_t* trail /* n_samples */);
+int pdsat_batch_trail(pdsat_batch* b, int32_t point, uint32_t* trail /* n_samples */);
 /* lbool bytes [n][n_vars] for samples first..first+n-1 of the point */
 int pdsat_batch_assign(pdsat_batch* b, int32_t point, uint64_t first, uint64_t n, uint8_t* assigns);
 /* models found by BCP alone (b_SAT_set_array, mpi_predicter.cpp:760-762): *n_found is the

@@ -29,7 +29,7 @@ EXPORTS = [
     "pdsat_batch_set_cost_buffer", "pdsat_batch_costs", "pdsat_batch_flags", "pdsat_batch_trail",
     "pdsat_batch_assign", "pdsat_batch_models", "pdsat_batch_destroy", "pdsat_eval_batch",
     "pdsat_mt19937_bool_rand", "pdsat_batch_peer_export", "pdsat_batch_peer_connect",
-    "pdsat_batch_peer_disconnect", "pdsat_batch_h2d_bytes",
+    "pdsat_batch_peer_disconnect", "pdsat_batch_h2d_bytes", "pdsat_db_gates", "pdsat_batch_set_first_draw",
 ]
 
 
@@ -41,7 +41,8 @@ class PdsatError(RuntimeError):
 
 class CPoint(C.Structure):
     _fields_ = [("set_vars", C.c_void_p), ("k", C.c_int32), ("mode", C.c_int32), ("seed", C.c_uint64),
-                ("first_sample", C.c_uint64), ("n_samples", C.c_uint64), ("explicit_values", C.c_void_p)]
+                ("first_sample", C.c_uint64), ("n_samples", C.c_uint64), ("explicit_values", C.c_void_p),
+                ("first_draw", C.c_uint64)]
 
 
 class CCost(C.Structure):
@@ -54,7 +55,13 @@ class CDbInfo(C.Structure):
     _fields_ = [("n_vars", C.c_int32), ("n_live_vars", C.c_int32), ("n_clauses_in", C.c_int64),
                 ("n_clauses_live", C.c_int64), ("n_lits_live", C.c_int64), ("n_base_assigned", C.c_int32),
                 ("max_clause_len", C.c_int32), ("status", C.c_int32), ("warps_per_cta", C.c_int32),
-                ("smem_bytes", C.c_int32), ("grid", C.c_int32), ("db_in_smem", C.c_int32), ("sm_count", C.c_int32)]
+                ("smem_bytes", C.c_int32), ("grid", C.c_int32), ("db_in_smem", C.c_int32), ("sm_count", C.c_int32),
+                ("n_gates", C.c_int32), ("blob_bytes", C.c_int32), ("n_gate_clauses", C.c_int64)]
+
+
+class CGate(C.Structure):
+    _fields_ = [("type", C.c_int32), ("parity", C.c_int32), ("m", C.c_int32), ("n_clauses", C.c_int32),
+                ("x", C.c_int32 * 7), ("lb", C.c_int32), ("lc", C.c_int32)]
 
 
 _lib = None
@@ -101,6 +108,8 @@ def lib():
     L.pdsat_batch_peer_connect.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
     L.pdsat_batch_peer_disconnect.argtypes = [C.c_void_p]
     L.pdsat_batch_h2d_bytes.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
+    L.pdsat_db_gates.argtypes = [C.c_void_p, C.c_int32, C.POINTER(CGate), C.POINTER(C.c_int32)]
+    L.pdsat_batch_set_first_draw.argtypes = [C.c_void_p, C.c_int32, C.c_uint64]
     _lib = L
     return L
 
@@ -125,6 +134,7 @@ class Point:
     seed: int = 1
     first_sample: int = 0
     explicit_values: Optional[np.ndarray] = None  # [n_samples, k] of {0,1}
+    first_draw: int = 0  # MT19937: draws the worker's generator has already made
 
 
 @dataclass
@@ -151,6 +161,7 @@ def _cpoints(points: Sequence[Point]):
         arr[i].seed = p.seed
         arr[i].first_sample = p.first_sample
         arr[i].n_samples = p.n_samples
+        arr[i].first_draw = p.first_draw
         if p.explicit_values is not None:
             ev = np.ascontiguousarray(p.explicit_values, dtype=np.uint8)
             assert ev.size == p.n_samples * len(sv)
@@ -194,6 +205,13 @@ class ClauseDb:
         _check(lib().pdsat_db_get_info(self.h, C.byref(i)))
         return i
 
+    def gates(self) -> List[CGate]:
+        n = C.c_int32(0)
+        _check(lib().pdsat_db_gates(self.h, 0, None, C.byref(n)))
+        arr = (CGate * max(n.value, 1))()
+        _check(lib().pdsat_db_gates(self.h, n.value, arr, C.byref(n)))
+        return [arr[i] for i in range(n.value)]
+
     def base_assignment(self) -> np.ndarray:
         a = np.empty(self.n_vars, dtype=np.uint8)
         _check(lib().pdsat_db_base_assignment(self.h, a.ctypes.data))
@@ -233,6 +251,9 @@ class Batch:
 
     def reseed(self, point: int, seed: int, first_sample: int) -> None:
         _check(lib().pdsat_batch_reseed(self.h, point, seed, first_sample))
+
+    def set_first_draw(self, point: int, first_draw: int) -> None:
+        _check(lib().pdsat_batch_set_first_draw(self.h, point, first_draw))
 
     def fill(self) -> None:
         _check(lib().pdsat_batch_fill(self.h))
@@ -303,7 +324,7 @@ class Batch:
         return cb, fb
 
     def trail(self, point: int = 0) -> np.ndarray:
-        t = np.empty(self.points[point].n_samples, dtype=np.uint16)
+        t = np.empty(self.points[point].n_samples, dtype=np.uint32)
         _check(lib().pdsat_batch_trail(self.h, point, t.ctypes.data))
         return t
 

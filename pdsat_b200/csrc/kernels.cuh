@@ -6,9 +6,11 @@
 //                       as a packed bit stream, 624 draws per round per stream segment
 //   bcp_kernel          bit-sliced unit propagation: one warp owns one group of 64 samples,
 //                       the assignment lives in shared memory as one 64-bit plane per
-//                       literal, lanes evaluate different clauses of an occurrence list
+//                       literal, lanes evaluate different gates / clauses of an occurrence list
 //                       (semantics of Solver::propagate, src_common/minisat/core/Solver.cc:599-662,
-//                       to the fixpoint / first conflict)
+//                       to the fixpoint / first conflict); the index blob of the database is
+//                       staged into shared memory and the assumption words are streamed in by
+//                       bulk async copies (cp.async.bulk + mbarrier)
 //
 // No tensor cores: nothing here is a contraction (integer / bit work bound by on-chip
 // memory and the LSU).
@@ -21,14 +23,20 @@ namespace pdsat {
 // ------------------------------------------------------------------ device views
 struct DbDev {
     const uint4* rec;         // 16-byte clause records: 8 x uint16 FALSE-plane codes (chains for > 8 literals)
-    const uint32_t* occ_off;  // [2*n_live+1]
     const uint4* occrec;      // per literal: the RECORDS of the clauses containing it, inline
                               // (a clause of > 8 literals appears as an indirect record -> rec[])
-    int32_t occ_off_in_smem;  // occ_off staged in shared memory (one copy per CTA)
+    // index blob (host_db.hpp): [occ_off u32[2*n_live+1]] [gocc_off u32[n_live+1]] [gocc u16[]]
+    // [gate records uint4[]], sections 16-byte aligned; staged into shared memory when it fits
+    const unsigned char* blob;
+    uint32_t blob_bytes;
+    uint32_t off_gocc_off, off_gocc, off_grec;
+    int32_t blob_in_smem;
     int32_t n_live;
     int32_t n_lit;            // 2*n_live
     int32_t n_base_assigned;
     int32_t unsat;            // level-0 conflict: every sample is a conflict
+    int32_t n_gates;
+    int32_t n_rec;            // clause records (0: every clause lives in a gate)
 };
 
 struct PointDev {
@@ -43,9 +51,12 @@ struct PointDev {
     uint32_t var_off;      // offset into the set-code table
     uint32_t mode;
     uint32_t n_assumed_live;  // set variables that are not fixed at level 0
-    uint32_t cand_off;        // first-wave candidate clauses of this point
+    uint32_t cand_off;        // first-wave candidate records (gates first, then clauses)
     uint32_t cand_cnt;
+    uint32_t kp;              // words per group in `words`: k rounded up to even (16-byte tiles)
+    uint32_t flags;           // POINT_*
 };
+static constexpr uint32_t POINT_HAS_FIXED = 1u;  // some set variable is assigned at level 0
 
 static constexpr uint32_t SETCODE_FIXED = 0x80000000u;  // set var already assigned at level 0; bit0 = its lbool
 
@@ -78,7 +89,7 @@ struct BatchDev {
     unsigned long long* cost;   // n_points * 8
     uint64_t* conflict_bits;    // per global group (optional)
     uint64_t* full_bits;        // per global group (optional)
-    uint16_t* trail;            // per global group * 64 (optional)
+    uint32_t* trail;            // per global group * 64 (optional)
     uint64_t* assign;           // per global group * n_lit (optional)
     unsigned long long* model_count;
     uint32_t* model_bits;       // max_models * model_words
@@ -86,6 +97,9 @@ struct BatchDev {
     uint64_t* model_sample;
     int32_t max_models;
     int32_t model_words;
+    // per-warp ring of assumption-word tiles (bulk async copies): stages x stage_bytes
+    int32_t ring_stages;
+    int32_t ring_stage_bytes;
     // fused cost all-reduce over NVLink peer memory (0 ranks = off, see PeerDev)
     PeerDev peer;
 };
@@ -109,7 +123,8 @@ __host__ __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
 
 // ------------------------------------------------------------------ fill
 // One thread per assumption word.  Word (group gi of point p, set position j) collects the
-// value of set variable j in samples 64*gi .. 64*gi+63.
+// value of set variable j in samples 64*gi .. 64*gi+63.  A group owns kp = k rounded up to even
+// words, so that every group tile is 16-byte aligned for the bulk copies of bcp_kernel.
 __global__ void fill_words_kernel(BatchDev b) {
     uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= b.n_words) return;
@@ -122,11 +137,12 @@ __global__ void fill_words_kernel(BatchDev b) {
     }
     const PointDev& pt = b.points[lo];
     uint64_t rel = w - pt.word_off;
-    uint64_t gi = rel / pt.k;
-    uint32_t j = (uint32_t)(rel - gi * pt.k);
+    uint64_t gi = rel / pt.kp;
+    uint32_t j = (uint32_t)(rel - gi * pt.kp);
     uint64_t s0 = gi * 64;
     uint64_t out = 0;
-    if (pt.mode == 1) {  // PDSAT_MODE_RANDOM_COUNTER
+    if (j >= pt.k) {  // padding word of an odd k
+    } else if (pt.mode == 1) {  // PDSAT_MODE_RANDOM_COUNTER
         uint64_t g = pt.first_sample / 64 + gi;
         out = splitmix64(pt.seed + 0x9E3779B97F4A7C15ull * (g * 65536ull + j + 1));
     } else if (pt.mode == 2) {  // PDSAT_MODE_ENUM
@@ -384,19 +400,54 @@ __global__ void __launch_bounds__(MT_BITS_WARPS * 32) mt19937_bits_kernel(const 
     }
 }
 
+// ------------------------------------------------------------------ bulk async copies (TMA) + mbarrier
+// 1-D bulk copies global -> shared issued by ONE thread and tracked by an mbarrier
+// (cp.async.bulk, SASS UBLKCP): used to stage the index blob of the clause database into shared
+// memory and to stream the assumption words of the next groups behind the propagation.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+
 // ------------------------------------------------------------------ BCP
 // Per-warp working set in shared memory (one warp owns one group of 64 samples):
-//   S[l]      64-bit plane per literal: samples in which literal l is TRUE
-//   queue     ring of implied literals whose occurrence lists still have to be visited
-//   touched   log of the literals implied in this group (undo list: only these planes and
-//             the assumption planes are cleared before the next group)
-//   inq       bitset "literal is in the queue"
+//   S[l]      64-bit plane per literal: samples in which literal l is TRUE.  S[2v], S[2v+1] (the
+//             TRUE and FALSE plane of variable v) are adjacent: one 16-byte load fetches both
+//   queue     ring of implied literals whose occurrence lists still have to be visited; after the
+//             fixpoint the same array holds the compacted list of implied literals (undo list)
+//   inq       bitset "literal is in the queue";  tset  bitset "literal was implied in this group"
+//   ring      multi-stage ring of assumption-word tiles filled by bulk async copies
 struct WarpCtx {
     uint64_t* S;
     uint16_t* queue;
-    uint16_t* touched;
     uint32_t* inq;
-    uint32_t* tset;     // bitset "literal is in the undo log"
+    uint32_t* tset;
     uint64_t* dead;     // samples in conflict
     uint32_t* qtail;
     uint32_t* ntouched;
@@ -430,114 +481,181 @@ __device__ __forceinline__ void push_lit(const WarpCtx& c, uint32_t l) {
     }
 }
 
+// make literal l true in the samples `bits` (Solver.cc:579-585 uncheckedEnqueue, for up to 64
+// samples at once).  Planes only gain bits; a literal that gained a bit is logged once per group
+// and (re)queued, so every clause / gate that can react to it is visited again.
+__device__ __forceinline__ void set_true(const WarpCtx& c, uint32_t l, uint64_t bits) {
+    const uint64_t old = or64_shared(&c.S[l], bits);
+    if (bits & ~old) {
+        const uint32_t bit = 1u << (l & 31);
+        if (!(atomicOr(&c.tset[l >> 5], bit) & bit)) atomicAdd(c.ntouched, 1u);
+        push_lit(c, l);
+    }
+}
+
 __device__ __forceinline__ uint32_t rec_slot(const uint4& r, int j) {
     const uint32_t w = j < 2 ? r.x : (j < 4 ? r.y : (j < 6 ? r.z : r.w));
     return (j & 1) ? (w >> 16) : (w & 0xFFFFu);
 }
 
-// ge1 / ge2 = samples in which the clause has >= 1 / >= 2 non-false literals.  A record has
-// 8 slots, each the code of a literal's FALSE plane; unused slots point at the "always false"
-// pad plane (all ones), so the evaluation is branch-free.  Occurrence lists and candidate lists
-// hold the records themselves (one dependent L2 load per clause instead of two); a clause of
-// more than 8 literals is an INDIRECT record (slot 7 == REC_INDIRECT, first word = index of
-// its chain in rec[], where slot 7 == REC_CONT links to the next record).
-static constexpr uint32_t REC_CONT_D = 0xFFFEu, REC_INDIRECT_D = 0xFFFDu;
+// (S[code & ~1], S[code | 1]) with one 16-byte shared load
+__device__ __forceinline__ void ld_pair(const uint64_t* S, uint32_t code, uint64_t& even, uint64_t& odd) {
+    const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(S + (code & ~1u));
+    even = v.x;
+    odd = v.y;
+}
 
-__device__ __forceinline__ void accumulate_slot(const uint64_t* S, uint32_t m, uint64_t& ge1, uint64_t& ge2) {
-    const uint64_t nf = ~S[m];
+// Record kinds (slot 7): plain clause (a plane code), REC_CONT_D / REC_INDIRECT_D (clauses of more
+// than 8 literals: INDIRECT = first word is the index of the chain in rec[], CONT links the chain),
+// REC_GATE_XOR_D | p, REC_GATE_ANDXOR_D | p (gate records, see host_db.hpp).
+static constexpr uint32_t REC_CONT_D = 0xFFFEu, REC_INDIRECT_D = 0xFFFDu;
+static constexpr uint32_t REC_GATE_XOR_D = 0xFFF0u, REC_GATE_ANDXOR_D = 0xFFF2u, REC_TAG_MIN_D = 0xFFF0u;
+
+// Clause slots hold the code m of the literal's FALSE plane; its TRUE plane is m ^ 1.
+//   ge1 / ge2 = samples with >= 1 / >= 2 non-false literals,  sat = samples with a true literal
+// Unused slots point at the pad plane pair (FALSE plane all ones, TRUE plane zero).
+__device__ __forceinline__ void accumulate_slot(const uint64_t* S, uint32_t m, uint64_t& ge1, uint64_t& ge2,
+                                                uint64_t& sat) {
+    uint64_t e, o;
+    ld_pair(S, m, e, o);
+    const uint64_t f = (m & 1u) ? o : e, t = (m & 1u) ? e : o;
+    const uint64_t nf = ~f;
     ge2 |= ge1 & nf;
     ge1 |= nf;
+    sat |= t;
 }
 
-__device__ __forceinline__ void eval_chain(const uint4* __restrict__ rec, uint32_t cur, const uint64_t* S,
-                                           uint64_t& ge1, uint64_t& ge2) {
-    bool more;
-    do {
-        const uint4 r = __ldg(&rec[cur]);
-#pragma unroll
-        for (int j = 0; j < 7; j++) accumulate_slot(S, rec_slot(r, j), ge1, ge2);
-        const uint32_t m7 = rec_slot(r, 7);
-        more = m7 == REC_CONT_D;
-        if (!more) accumulate_slot(S, m7, ge1, ge2);
-        cur++;
-    } while (more);
-}
-
-__device__ __forceinline__ void eval_rec(const uint4& r, const uint4* __restrict__ rec, const uint64_t* S,
-                                         uint64_t& ge1, uint64_t& ge2) {
-    ge1 = 0;
-    ge2 = 0;
-    if (rec_slot(r, 7) == REC_INDIRECT_D) {
-        eval_chain(rec, r.x, S, ge1, ge2);
-    } else {
-#pragma unroll
-        for (int j = 0; j < 8; j++) accumulate_slot(S, rec_slot(r, j), ge1, ge2);
-    }
-}
-
-// make literal (plane m^1) true in the samples `imp` where it is still undefined
-__device__ __forceinline__ void imply_lit(const WarpCtx& c, uint32_t m, uint64_t imp) {
-    imp &= ~c.S[m ^ 1];
-    if (imp) {
-        const uint32_t l = m ^ 1;
-        const uint64_t old = or64_shared(&c.S[l], imp);
-        if (imp & ~old) {
-            // first time this literal is implied in the group: log it once (undo list)
-            const uint32_t bit = 1u << (l & 31);
-            if (!(atomicOr(&c.tset[l >> 5], bit) & bit)) c.touched[atomicAdd(c.ntouched, 1u)] = (uint16_t)l;
-            push_lit(c, l);
-        }
-    }
-}
-
+// in the samples of `unit` the clause has exactly one non-false literal and it is undefined: make
+// it true (Solver.cc:641-648 uncheckedEnqueue(first, cr))
 __device__ __forceinline__ void imply_slot(const WarpCtx& c, uint32_t m, uint64_t unit) {
     const uint64_t imp = unit & ~c.S[m];
-    if (imp) imply_lit(c, m, imp);
+    if (imp) set_true(c, m ^ 1u, imp);
 }
 
-// rare path: in the samples of `unit` the clause has exactly one non-false literal; make it
-// true where it is still undefined (Solver.cc:641-648 uncheckedEnqueue(first, cr))
-__device__ __forceinline__ void imply_from_rec(const uint4& r0, const uint4* __restrict__ rec, const WarpCtx& c,
-                                               uint64_t unit) {
-    if (rec_slot(r0, 7) == REC_INDIRECT_D) {
+__device__ __forceinline__ void eval_clause(const uint4& r0, const uint4* __restrict__ rec, const WarpCtx& c,
+                                            uint64_t live) {
+    uint64_t ge1 = 0, ge2 = 0, sat = 0;
+    const bool indirect = rec_slot(r0, 7) == REC_INDIRECT_D;
+    if (indirect) {
         uint32_t cur = r0.x;
         bool more;
         do {
             const uint4 r = __ldg(&rec[cur]);
 #pragma unroll
-            for (int j = 0; j < 7; j++) imply_slot(c, rec_slot(r, j), unit);
+            for (int j = 0; j < 7; j++) accumulate_slot(c.S, rec_slot(r, j), ge1, ge2, sat);
             const uint32_t m7 = rec_slot(r, 7);
             more = m7 == REC_CONT_D;
-            if (!more) imply_slot(c, m7, unit);
+            if (!more) accumulate_slot(c.S, m7, ge1, ge2, sat);
             cur++;
         } while (more);
     } else {
 #pragma unroll
-        for (int j = 0; j < 8; j++) imply_slot(c, rec_slot(r0, j), unit);
+        for (int j = 0; j < 8; j++) accumulate_slot(c.S, rec_slot(r0, j), ge1, ge2, sat);
     }
-}
-
-__device__ __forceinline__ void settle_rec(const uint4& r, const uint4* __restrict__ rec, const WarpCtx& c,
-                                           uint64_t live, uint64_t ge1, uint64_t ge2) {
     const uint64_t confl = ~ge1 & live;
-    const uint64_t unit = ge1 & ~ge2 & live;
+    const uint64_t unit = ge1 & ~ge2 & ~sat & live;
     if (confl) or64_shared(c.dead, confl);
-    if (unit) imply_from_rec(r, rec, c, unit);
+    if (unit) {
+        if (indirect) {
+            uint32_t cur = r0.x;
+            bool more;
+            do {
+                const uint4 r = __ldg(&rec[cur]);
+#pragma unroll
+                for (int j = 0; j < 7; j++) imply_slot(c, rec_slot(r, j), unit);
+                const uint32_t m7 = rec_slot(r, 7);
+                more = m7 == REC_CONT_D;
+                if (!more) imply_slot(c, m7, unit);
+                cur++;
+            } while (more);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; j++) imply_slot(c, rec_slot(r0, j), unit);
+        }
+    }
 }
 
-// visit the records list[0..n): two clauses per lane per trip so that their loads overlap
-__device__ __forceinline__ void visit_records(const uint4* __restrict__ rec, const uint4* __restrict__ list,
-                                              uint32_t n, const WarpCtx& c, uint64_t live, int lane) {
-    for (uint32_t i = lane; i < n; i += 64) {
-        const bool two = i + 32 < n;
-        const uint4 r0 = __ldg(&list[i]);
-        const uint4 r1 = __ldg(&list[two ? i + 32 : i]);
-        uint64_t a1, a2, b1, b2;
-        eval_rec(r0, rec, c.S, a1, a2);
-        eval_rec(r1, rec, c.S, b1, b2);
-        settle_rec(r0, rec, c, live, a1, a2);
-        if (two) settle_rec(r1, rec, c, live, b1, b2);
+// Gate in closed form on 64 samples.  XOR: x_0 ^ ... ^ x_6 = p.  ANDXOR: x_0 ^ ... ^ x_4 ^ q = p
+// with q = Lb & Lc (q is known 1 where both literals are true, known 0 where one is false).
+// With u_i = "x_i unknown":  conflict where nothing is unknown and the parity is wrong; where
+// exactly one member is unknown it takes the value  p ^ xor(known values).  For the product: q
+// must be 1 -> Lb and Lc become true; q must be 0 and one literal is true -> the other becomes
+// false.  Equal to unit propagation over the gate's clauses (tests/test_gates.py).
+__device__ __forceinline__ void imply_var(const WarpCtx& c, uint32_t tcode, uint64_t imp, uint64_t par) {
+    if (imp) {
+        const uint64_t t = imp & par, f = imp & ~par;
+        if (t) set_true(c, tcode, t);
+        if (f) set_true(c, tcode + 1u, f);
     }
+}
+
+__device__ __forceinline__ void eval_gate(const uint4& r, const WarpCtx& c, uint64_t live) {
+    const uint32_t tag = r.w >> 16;
+    const bool andxor = tag >= REC_GATE_ANDXOR_D;
+    uint64_t par = (tag & 1u) ? ~0ull : 0ull;  // p ^ xor(values): must end up 0
+    uint64_t any = 0, two = 0;
+    uint64_t u0, u1, u2, u3, u4, u5 = 0, u6 = 0, tb = 0, tc = 0, qu = 0;
+    uint64_t t, f;
+#define PDSAT_XVAR(U, CODE)              \
+    ld_pair(c.S, (CODE), t, f);          \
+    U = ~(t | f);                        \
+    par ^= t;                            \
+    two |= any & U;                      \
+    any |= U;
+    PDSAT_XVAR(u0, r.x & 0xFFFFu)
+    PDSAT_XVAR(u1, r.x >> 16)
+    PDSAT_XVAR(u2, r.y & 0xFFFFu)
+    PDSAT_XVAR(u3, r.y >> 16)
+    PDSAT_XVAR(u4, r.z & 0xFFFFu)
+    const uint32_t c5 = r.z >> 16, c6 = r.w & 0xFFFFu;
+    if (!andxor) {
+        PDSAT_XVAR(u5, c5)
+        PDSAT_XVAR(u6, c6)
+    } else {
+        uint64_t e, o;
+        ld_pair(c.S, c5, e, o);
+        tb = (c5 & 1u) ? o : e;
+        const uint64_t fb = (c5 & 1u) ? e : o;
+        ld_pair(c.S, c6, e, o);
+        tc = (c6 & 1u) ? o : e;
+        const uint64_t fc = (c6 & 1u) ? e : o;
+        const uint64_t q1 = tb & tc, q0 = fb | fc;
+        qu = ~(q1 | q0);
+        par ^= q1;
+        two |= any & qu;
+        any |= qu;
+    }
+#undef PDSAT_XVAR
+    const uint64_t confl = ~any & par & live;
+    const uint64_t one = any & ~two & live;
+    if (confl) or64_shared(c.dead, confl);
+    if (one) {
+        imply_var(c, r.x & 0xFFFFu, one & u0, par);
+        imply_var(c, r.x >> 16, one & u1, par);
+        imply_var(c, r.y & 0xFFFFu, one & u2, par);
+        imply_var(c, r.y >> 16, one & u3, par);
+        imply_var(c, r.z & 0xFFFFu, one & u4, par);
+        if (!andxor) {
+            imply_var(c, c5, one & u5, par);
+            imply_var(c, c6, one & u6, par);
+        } else {
+            const uint64_t iq = one & qu;
+            if (iq) {
+                const uint64_t s1 = iq & par, s0 = iq & ~par;
+                if (s1 & ~tb) set_true(c, c5, s1 & ~tb);
+                if (s1 & ~tc) set_true(c, c6, s1 & ~tc);
+                if (s0 & tb) set_true(c, c6 ^ 1u, s0 & tb);
+                if (s0 & tc) set_true(c, c5 ^ 1u, s0 & tc);
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ void eval_record(const uint4& r, const uint4* __restrict__ rec, const WarpCtx& c,
+                                            uint64_t live) {
+    const uint32_t tag = r.w >> 16;
+    if (tag >= REC_TAG_MIN_D && tag < REC_INDIRECT_D) eval_gate(r, c, live);
+    else eval_clause(r, rec, c, live);
 }
 
 __device__ __forceinline__ uint64_t shfl64(uint64_t v, int src) {
@@ -548,9 +666,14 @@ __device__ __forceinline__ uint64_t shfl_down64(uint64_t v, int d) {
     return ((uint64_t)__shfl_down_sync(0xffffffffu, (uint32_t)(v >> 32), d) << 32) |
            __shfl_down_sync(0xffffffffu, (uint32_t)v, d);
 }
+__device__ __forceinline__ uint64_t warp_sum64(uint64_t v) {
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) v += shfl_down64(v, off);
+    return shfl64(v, 0);
+}
 
 static constexpr int MAX_COUNT_BITS = 15;
-static constexpr int MULTI_POP = 8;  // queued literals processed per propagation round
+static constexpr int MULTI_POP = 32;  // queued literals processed per propagation round (one per lane)
 
 struct WarpAcc {
     uint64_t n, n_conflict, n_full, sum, sumsq, n_impl, pops, touched;
@@ -572,28 +695,112 @@ __device__ __forceinline__ void flush_acc(WarpAcc& a, unsigned long long* cost, 
     a.n = a.n_conflict = a.n_full = a.sum = a.sumsq = a.n_impl = a.pops = a.touched = 0;
 }
 
+// owner of flattened item i among the first MULTI_POP lanes' lists: the smallest q with
+// cum[q] > i (cum = inclusive prefix sums held one per lane)
+__device__ __forceinline__ int find_owner(uint32_t cum, uint32_t i) {
+    int lo = 0;
+#pragma unroll
+    for (int step = 16; step >= 1; step >>= 1) {
+        const uint32_t cmid = __shfl_sync(0xffffffffu, cum, lo + step - 1);
+        if (cmid <= i) lo += step;
+    }
+    return lo;
+}
+
+__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t up = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane >= d) v += up;
+    }
+    return v;
+}
+
+// per-sample count of set planes among the literals list[0..n): bit-sliced vertical counters of
+// NB bits (n < 2^NB), summed over the lanes; returns the counts of samples lane and lane + 32
+template <int NB>
+__device__ __forceinline__ void count_planes(const uint64_t* S, const uint16_t* list, uint32_t n, int lane,
+                                             uint32_t& cnt0, uint32_t& cnt1) {
+    uint64_t cb[NB];
+#pragma unroll
+    for (int q = 0; q < NB; q++) cb[q] = 0;
+    for (uint32_t i = lane; i < n; i += 32) {
+        uint64_t carry = S[list[i]];
+#pragma unroll
+        for (int q = 0; q < NB; q++) {
+            const uint64_t t = cb[q] & carry;
+            cb[q] ^= carry;
+            carry = t;
+        }
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        uint64_t carry = 0;
+#pragma unroll
+        for (int q = 0; q < NB; q++) {
+            const uint64_t o = shfl_down64(cb[q], off);
+            const uint64_t x = cb[q] ^ o;
+            const uint64_t s = x ^ carry;
+            carry = (cb[q] & o) | (carry & x);
+            cb[q] = s;
+        }
+    }
+    cnt0 = cnt1 = 0;
+#pragma unroll
+    for (int q = 0; q < NB; q++) {
+        const uint64_t t = shfl64(cb[q], 0);
+        cnt0 |= (uint32_t)((t >> lane) & 1ull) << q;
+        cnt1 |= (uint32_t)((t >> (lane + 32)) & 1ull) << q;
+    }
+}
+
 // Persistent kernel: grid = #SMs, each warp strides over the 64-sample groups.
 //
-// Per group:  (1) write the assumption planes;  (2) FIRST WAVE: visit the point's candidate
-// clauses - the only clauses that can be unit or falsified when just the set variables are
-// assigned are those with at most one literal outside the set (computed once per point on
-// the host; MiniSat gets the same effect lazily from its two watched literals);
-// (3) drain the queue of implied literals, visiting every clause that contains the
-// complement of a literal that became true (Solver.cc:611-655);  (4) per-sample results and
-// integer cost accumulation;  (5) undo: clear only the planes that were written.
+// Per group:  (0) the group's assumption words arrive through the warp's bulk-copy ring (tiles
+// of the next `stages` groups are in flight behind the propagation);  (1) write the assumption
+// planes;  (2) FIRST WAVE: visit the point's candidate records - the only clauses / gates that
+// can be unit or falsified when just the set variables are assigned (computed once per point on
+// the host; MiniSat gets the same effect lazily from its two watched literals);  (3) drain the
+// queue of implied literals, visiting every gate that contains the variable and every clause that
+// contains the complement of a literal that became true (Solver.cc:611-655);  (4) per-sample
+// results and integer cost accumulation;  (5) undo: clear only the planes that were written.
+// A point without candidates and without level-0-fixed set variables cannot start BCP at all:
+// its groups skip (1), (2), (3) and (5) - the words still stream through the ring.
 __global__ void __launch_bounds__(512, 1)
 bcp_kernel(DbDev db, BatchDev b, int warp_bytes, int qcap) {
     extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ __align__(8) uint64_t blob_bar;
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int wpc = blockDim.x >> 5;
-    unsigned char* base = smem + (size_t)warp * warp_bytes;
+
+    // ---- index blob (occurrence offsets, gate lists, gate records): one bulk copy per CTA into
+    // shared memory when it fits, otherwise read from global / L2
+    const unsigned char* blob = db.blob;
+    const int blob_smem_bytes = db.blob_in_smem ? (int)db.blob_bytes : 0;
+    if (db.blob_in_smem) {
+        if (threadIdx.x == 0) {
+            mbar_init(&blob_bar, 1);
+            mbar_fence_init();
+            mbar_expect_tx(&blob_bar, db.blob_bytes);
+            for (uint32_t off = 0; off < db.blob_bytes; off += 32768u) {
+                const uint32_t n = min(32768u, db.blob_bytes - off);
+                bulk_g2s(smem + off, db.blob + off, n, &blob_bar);
+            }
+        }
+        blob = smem;
+    }
+    const uint32_t* occ_off = (const uint32_t*)blob;
+    const uint32_t* gocc_off = (const uint32_t*)(blob + db.off_gocc_off);
+    const uint16_t* gocc = (const uint16_t*)(blob + db.off_gocc);
+    const uint4* grec = (const uint4*)(blob + db.off_grec);
+
+    unsigned char* base = smem + blob_smem_bytes + (size_t)warp * warp_bytes;
     WarpCtx c;
     c.S = (uint64_t*)base;
-    const int n_planes = db.n_lit + 2;
+    const int n_planes = db.n_lit + 4;
     c.queue = (uint16_t*)(c.S + n_planes);
-    c.touched = c.queue + qcap;                 // qcap ring slots (one per literal, multiple of 4)
-    c.inq = (uint32_t*)(c.touched + ((db.n_lit + 2 + 3) & ~3));
+    c.inq = (uint32_t*)(c.queue + qcap);  // qcap ring slots (one per literal, multiple of 4)
     const int inq_words = (db.n_lit + 31) >> 5;
     c.tset = c.inq + ((inq_words + 1) & ~1);
     c.dead = (uint64_t*)(c.tset + ((inq_words + 1) & ~1));
@@ -601,22 +808,22 @@ bcp_kernel(DbDev db, BatchDev b, int warp_bytes, int qcap) {
     c.ntouched = c.qtail + 1;
     c.qcap = (uint32_t)qcap;
     c.qmagic = (uint32_t)((0x100000000ull + (uint32_t)qcap - 1) / (uint32_t)qcap);
+    // 16-byte aligned: mbarriers, then the tiles the bulk copies write
+    uint64_t* ring_bar = (uint64_t*)(base + ((((unsigned char*)(c.qtail + 2) - base) + 15) & ~(size_t)15));
+    const int stages = b.ring_stages;
+    unsigned char* ring = (unsigned char*)(ring_bar + ((stages + 1) & ~1));
 
-    // occurrence offsets: one copy per CTA in shared memory when it fits (saves a dependent L2
-    // round trip per propagation round)
-    const uint32_t* occ_off = db.occ_off;
-    if (db.occ_off_in_smem) {
-        uint32_t* so = (uint32_t*)(smem + (size_t)wpc * warp_bytes);
-        for (int i = threadIdx.x; i <= db.n_lit; i += blockDim.x) so[i] = db.occ_off[i];
-        __syncthreads();
-        occ_off = so;
-    }
-
-    // the planes start clean and every group cleans up after itself
-    for (int i = lane; i < n_planes; i += 32) c.S[i] = i == db.n_lit ? ~0ull : 0ull;  // plane n_lit = pad
+    // the planes start clean and every group cleans up after itself; pads: plane n_lit = "always
+    // false" literal (FALSE plane all ones, TRUE plane 0), n_lit + 2 / + 3 = the pad variable of
+    // gate records (TRUE plane 0, FALSE plane all ones: known, value 0)
+    for (int i = lane; i < n_planes; i += 32) c.S[i] = (i == db.n_lit || i == db.n_lit + 3) ? ~0ull : 0ull;
     for (int i = lane; i < inq_words; i += 32) {
         c.inq[i] = 0;
         c.tset[i] = 0;
+    }
+    if (lane == 0) {
+        for (int s = 0; s < stages; s++) mbar_init(&ring_bar[s], 1);
+        mbar_fence_init();
     }
     __syncwarp();
 
@@ -625,29 +832,60 @@ bcp_kernel(DbDev db, BatchDev b, int warp_bytes, int qcap) {
     acc.point = -1;
 
     const uint64_t stride = (uint64_t)gridDim.x * wpc;
+    const uint64_t g_first = (uint64_t)blockIdx.x * wpc + warp;
+
+    // ---- producer side of the words ring (lane 0): group g_pf goes to stage pf_stage
+    uint64_t pf_g = g_first;
+    int pf_stage = 0;
+    int pf_p = -1;
+    uint64_t pf_start = 0, pf_end = 0, pf_word_off = 0;
+    uint32_t pf_kp = 0;
+    auto prefetch_one = [&]() {
+        if (pf_g < b.n_groups) {
+            if (pf_p < 0 || pf_g >= pf_end) {
+                pf_p = find_point(b.points, b.n_points, pf_g);
+                const PointDev* pt = &b.points[pf_p];
+                pf_start = pt->group_start;
+                pf_end = pf_p + 1 < b.n_points ? b.points[pf_p + 1].group_start : b.n_groups;
+                pf_word_off = pt->word_off;
+                pf_kp = pt->kp;
+            }
+            const uint32_t bytes = pf_kp * 8u;
+            mbar_expect_tx(&ring_bar[pf_stage], bytes);
+            bulk_g2s(ring + (size_t)pf_stage * b.ring_stage_bytes, b.words + pf_word_off + (pf_g - pf_start) * pf_kp, bytes,
+                     &ring_bar[pf_stage]);
+        }
+        pf_g += stride;
+        pf_stage = pf_stage + 1 == stages ? 0 : pf_stage + 1;
+    };
+    if (lane == 0)
+        for (int s = 0; s < stages; s++) prefetch_one();
+
+    if (db.blob_in_smem) {
+        __syncthreads();  // the barrier init is visible to everybody
+        mbar_wait(&blob_bar, 0);
+    }
+
     // current point, cached in registers (a warp usually stays inside one point for many groups)
     int p = -1;
-    uint64_t P_start = 0, P_end = 0, P_word_off = 0, P_n_samples = 0;
-    uint32_t k = 0, P_var_off = 0, P_n_assumed = 0, P_cand_off = 0, P_cand_cnt = 0, P_code0 = 0;
-    // software prefetch: the word of set position `lane` of the NEXT group is requested while
-    // the current group is processed (the per-group critical path is this HBM load)
-    uint64_t pf_bits = 0;
-    bool pf_valid = false;
-    for (uint64_t g = (uint64_t)blockIdx.x * wpc + warp; g < b.n_groups; g += stride) {
+    uint64_t P_start = 0, P_end = 0, P_n_samples = 0;
+    uint32_t k = 0, P_var_off = 0, P_n_assumed = 0, P_cand_off = 0, P_cand_cnt = 0, P_code0 = 0, P_flags = 0;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (uint64_t g = g_first; g < b.n_groups; g += stride) {
         if (p < 0 || g >= P_end) {
             p = find_point(b.points, b.n_points, g);
             const PointDev* pt = &b.points[p];
             P_start = pt->group_start;
             P_end = p + 1 < b.n_points ? b.points[p + 1].group_start : b.n_groups;
-            P_word_off = pt->word_off;
             P_n_samples = pt->n_samples;
             k = pt->k;
             P_var_off = pt->var_off;
             P_n_assumed = pt->n_assumed_live;
             P_cand_off = pt->cand_off;
             P_cand_cnt = pt->cand_cnt;
+            P_flags = pt->flags;
             P_code0 = lane < (int)k ? b.setcode[P_var_off + lane] : 0u;
-            pf_valid = false;
             flush_acc(acc, b.cost, lane);
             acc.point = p;
         }
@@ -656,96 +894,111 @@ bcp_kernel(DbDev db, BatchDev b, int warp_bytes, int qcap) {
         const uint64_t left = P_n_samples - s0;
         const uint64_t valid = left >= 64 ? ~0ull : ((1ull << left) - 1);
         const uint32_t* code = b.setcode + P_var_off;
-        const uint64_t* w = b.words + P_word_off + gi * k;
-        uint64_t bits0 = pf_bits;
-        if (!pf_valid && lane < (int)k) bits0 = w[lane];
-        {
-            const uint64_t gn = g + stride;
-            pf_valid = gn < P_end;
-            if (pf_valid && lane < (int)k) pf_bits = b.words[P_word_off + (gn - P_start) * k + lane];
-        }
+        const uint64_t* w = (const uint64_t*)(ring + (size_t)stage * b.ring_stage_bytes);
+        // BCP can only start from a candidate record or a contradicted level-0 value
+        const bool active = !db.unsat && (P_cand_cnt != 0 || (P_flags & POINT_HAS_FIXED) != 0 || b.assign != nullptr);
 
         if (lane == 0) {
             *c.dead = db.unsat ? valid : 0;
             *c.qtail = 0;
             *c.ntouched = 0;
         }
+        mbar_wait(&ring_bar[stage], phase);  // the group's words have landed
         __syncwarp();
 
         // ---- (1) assumptions (src_mpi/mpi_predicter.cpp:3236-3242: true bit => positive literal)
-        if (!db.unsat) {
+        if (active) {
             for (uint32_t j = lane; j < k; j += 32) {
                 const uint32_t cd = j < 32 ? P_code0 : code[j];
-                const uint64_t bits = j < 32 ? bits0 : w[j];
+                const uint64_t bits = w[j];
                 if (cd & SETCODE_FIXED) {
                     // variable already assigned at level 0: a contradicting value is a
                     // conflict (addClause_ drops the false literal: empty clause)
                     const uint64_t bad = ((cd & 1u) ? bits : ~bits) & valid;
                     if (bad) or64_shared(c.dead, bad);
                 } else {
-                    c.S[cd] = bits & valid;
-                    c.S[cd ^ 1] = ~bits & valid;
+                    ulonglong2 tf;
+                    tf.x = bits & valid;
+                    tf.y = ~bits & valid;
+                    *reinterpret_cast<ulonglong2*>(c.S + cd) = tf;  // cd is even: TRUE / FALSE pair
                 }
             }
-            __syncwarp();
+        }
+        __syncwarp();
+        // the stage is free again: request the tile `stages` groups ahead
+        if (lane == 0) prefetch_one();
+        stage = stage + 1 == stages ? 0 : stage + 1;
+        phase ^= (stage == 0);
 
-            // ---- (2) first wave over the point's candidate clauses
+        uint32_t qh = 0;
+        if (active) {
+            // ---- (2) first wave over the point's candidate records
             if (P_cand_cnt) {
                 const uint64_t live = valid & ~*(volatile uint64_t*)c.dead;
-                visit_records(db.rec, b.cand + P_cand_off, P_cand_cnt, c, live, lane);
+                const uint4* list = b.cand + P_cand_off;
+                uint4 r = __ldg(&list[min((uint32_t)lane, P_cand_cnt - 1)]);
+                for (uint32_t i = lane; i < P_cand_cnt; i += 32) {
+                    const uint4 cur = r;
+                    if (i + 32 < P_cand_cnt) r = __ldg(&list[i + 32]);
+                    eval_record(cur, db.rec, c, live);
+                }
                 __syncwarp();
             }
 
-            // ---- (3) propagate the implied literals to the fixpoint.  Up to MULTI_POP
-            // queued literals are taken per round; their occurrence lists are visited as one
-            // concatenated list so that the dependent loads of several literals overlap.
-            uint32_t qh = 0;
+            // ---- (3) propagate the implied literals to the fixpoint.  Up to 32 queued literals
+            // are taken per round (one per lane); the gate lists of their variables, then the
+            // clause lists of their complements, are visited as one flattened list each, one
+            // record per lane per trip.
             while (true) {
                 const uint32_t qt = *(volatile uint32_t*)c.qtail;
                 const uint64_t deadv = *(volatile uint64_t*)c.dead;
                 if (qh == qt || (deadv & valid) == valid) break;
                 const uint32_t np = min(qt - qh, (uint32_t)MULTI_POP);
-                uint32_t myl = 0, mybeg = 0, mylen = 0;
+                uint32_t myl = 0, gbeg = 0, glen = 0, cbeg = 0, clen = 0;
                 if (lane < (int)np) myl = c.queue[ring_index(c, qh + lane)];
                 qh += np;
                 __syncwarp();
                 if (lane < (int)np) {
                     atomicAnd(&c.inq[myl >> 5], ~(1u << (myl & 31)));
-                    const uint32_t nl = myl ^ 1;  // this literal just became false somewhere
-                    mybeg = occ_off[nl];
-                    mylen = occ_off[nl + 1] - mybeg;
-                }
-                uint32_t cum = mylen;  // inclusive scan over the first MULTI_POP lanes
-#pragma unroll
-                for (int d = 1; d < MULTI_POP; d <<= 1) {
-                    const uint32_t up = __shfl_up_sync(0xffffffffu, cum, d);
-                    if (lane >= d) cum += up;
-                }
-                const uint32_t total = __shfl_sync(0xffffffffu, cum, MULTI_POP - 1);
-                uint32_t bound[MULTI_POP], base[MULTI_POP];
-#pragma unroll
-                for (int q = 0; q < MULTI_POP; q++) {
-                    bound[q] = __shfl_sync(0xffffffffu, cum, q);
-                    base[q] = __shfl_sync(0xffffffffu, mybeg - (cum - mylen), q);  // occ index = base + i
-                }
-                __syncwarp();
-                const uint64_t live = valid & ~deadv;
-                for (uint32_t i = lane; i < total; i += 64) {
-                    const bool two = i + 32 < total;
-                    const uint32_t i1 = two ? i + 32 : i;
-                    uint32_t o0 = base[0], o1 = base[0];
-#pragma unroll
-                    for (int q = 1; q < MULTI_POP; q++) {
-                        if (i >= bound[q - 1]) o0 = base[q];
-                        if (i1 >= bound[q - 1]) o1 = base[q];
+                    if (db.n_gates) {
+                        const uint32_t v = myl >> 1;
+                        gbeg = gocc_off[v];
+                        glen = gocc_off[v + 1] - gbeg;
                     }
-                    const uint4 r0 = __ldg(&db.occrec[o0 + i]);
-                    const uint4 r1 = __ldg(&db.occrec[o1 + i1]);
-                    uint64_t a1, a2, b1, b2;
-                    eval_rec(r0, db.rec, c.S, a1, a2);
-                    eval_rec(r1, db.rec, c.S, b1, b2);
-                    settle_rec(r0, db.rec, c, live, a1, a2);
-                    if (two) settle_rec(r1, db.rec, c, live, b1, b2);
+                    if (db.n_rec) {
+                        const uint32_t nl = myl ^ 1;  // this literal just became false somewhere
+                        cbeg = occ_off[nl];
+                        clen = occ_off[nl + 1] - cbeg;
+                    }
+                }
+                const uint64_t live = valid & ~deadv;
+                if (db.n_gates) {
+                    const uint32_t cum = warp_incl_scan(glen, lane);
+                    const uint32_t total = __shfl_sync(0xffffffffu, cum, 31);
+                    const uint32_t gbase = gbeg - (cum - glen);  // list index = gbase + i
+                    for (uint32_t i0 = 0; i0 < total; i0 += 32) {
+                        const uint32_t i = i0 + lane;
+                        const int q = find_owner(cum, i);
+                        const uint32_t bq = __shfl_sync(0xffffffffu, gbase, q & 31);
+                        if (i < total) {
+                            const uint4 r = grec[gocc[bq + i]];
+                            eval_gate(r, c, live);
+                        }
+                    }
+                }
+                if (db.n_rec) {
+                    const uint32_t cum = warp_incl_scan(clen, lane);
+                    const uint32_t total = __shfl_sync(0xffffffffu, cum, 31);
+                    const uint32_t cbase = cbeg - (cum - clen);
+                    for (uint32_t i0 = 0; i0 < total; i0 += 32) {
+                        const uint32_t i = i0 + lane;
+                        const int q = find_owner(cum, i);
+                        const uint32_t bq = __shfl_sync(0xffffffffu, cbase, q & 31);
+                        if (i < total) {
+                            const uint4 r = __ldg(&db.occrec[bq + i]);
+                            eval_clause(r, db.rec, c, live);
+                        }
+                    }
                 }
                 __syncwarp();
             }
@@ -762,40 +1015,28 @@ bcp_kernel(DbDev db, BatchDev b, int warp_bytes, int qcap) {
         if (n_touched == 0) {
             cnt0 = cnt1 = P_n_assumed;
         } else {
+            // compact the implied literals (bits of tset) into the now idle queue array
+            uint32_t basew = 0;
+            for (int w0 = 0; w0 < inq_words; w0 += 32) {
+                const int wi = w0 + lane;
+                uint32_t bits = wi < inq_words ? c.tset[wi] : 0u;
+                const uint32_t pc = __popc(bits);
+                const uint32_t incl = warp_incl_scan(pc, lane);
+                uint32_t o = basew + incl - pc;
+                while (bits) {
+                    const int bpos = __ffs(bits) - 1;
+                    bits &= bits - 1;
+                    c.queue[o++] = (uint16_t)(32 * wi + bpos);
+                }
+                basew += __shfl_sync(0xffffffffu, incl, 31);
+            }
+            __syncwarp();
             // bit-sliced population count over the implied planes: per sample, how many
             // literals of the undo list are set (each implied variable has one polarity per
             // conflict-free sample)
-            uint64_t cb[MAX_COUNT_BITS];
-#pragma unroll
-            for (int q = 0; q < MAX_COUNT_BITS; q++) cb[q] = 0;
-            for (uint32_t i = lane; i < n_touched; i += 32) {
-                uint64_t carry = c.S[c.touched[i]];
-#pragma unroll
-                for (int q = 0; q < MAX_COUNT_BITS; q++) {
-                    const uint64_t t = cb[q] & carry;
-                    cb[q] ^= carry;
-                    carry = t;
-                }
-            }
-#pragma unroll
-            for (int off = 16; off >= 1; off >>= 1) {
-                uint64_t carry = 0;
-#pragma unroll
-                for (int q = 0; q < MAX_COUNT_BITS; q++) {
-                    const uint64_t o = shfl_down64(cb[q], off);
-                    const uint64_t x = cb[q] ^ o;
-                    const uint64_t s = x ^ carry;
-                    carry = (cb[q] & o) | (carry & x);
-                    cb[q] = s;
-                }
-            }
-            cnt0 = cnt1 = 0;
-#pragma unroll
-            for (int q = 0; q < MAX_COUNT_BITS; q++) {
-                const uint64_t t = shfl64(cb[q], 0);
-                cnt0 |= (uint32_t)((t >> lane) & 1ull) << q;
-                cnt1 |= (uint32_t)((t >> (lane + 32)) & 1ull) << q;
-            }
+            if (n_touched < 256) count_planes<8>(c.S, c.queue, n_touched, lane, cnt0, cnt1);
+            else if (n_touched < 2048) count_planes<11>(c.S, c.queue, n_touched, lane, cnt0, cnt1);
+            else count_planes<MAX_COUNT_BITS>(c.S, c.queue, n_touched, lane, cnt0, cnt1);
             cnt0 += P_n_assumed;
             cnt1 += P_n_assumed;
         }
@@ -809,11 +1050,13 @@ bcp_kernel(DbDev db, BatchDev b, int warp_bytes, int qcap) {
             acc.sum += nok * t0;
             acc.sumsq += nok * (uint64_t)t0 * t0;
         } else {
-            uint32_t lsum = (ok0 ? t0 : 0) + (ok1 ? t1 : 0);
-            uint32_t lsq = (ok0 ? t0 * t0 : 0) + (ok1 ? t1 * t1 : 0);
-            uint32_t limp = (ok0 && cnt0 > P_n_assumed ? 1 : 0) + (ok1 && cnt1 > P_n_assumed ? 1 : 0);
-            acc.sum += __reduce_add_sync(0xffffffffu, lsum);
-            acc.sumsq += __reduce_add_sync(0xffffffffu, lsq);
+            // 64-bit throughout: trail can reach n_vars, its square summed over 64 samples
+            // does not fit 32 bits from trail = 8192 on
+            const uint64_t lsum = (ok0 ? (uint64_t)t0 : 0ull) + (ok1 ? (uint64_t)t1 : 0ull);
+            const uint64_t lsq = (ok0 ? (uint64_t)t0 * t0 : 0ull) + (ok1 ? (uint64_t)t1 * t1 : 0ull);
+            const uint32_t limp = (ok0 && cnt0 > P_n_assumed ? 1 : 0) + (ok1 && cnt1 > P_n_assumed ? 1 : 0);
+            acc.sum += warp_sum64(lsum);
+            acc.sumsq += warp_sum64(lsq);
             acc.n_impl += __reduce_add_sync(0xffffffffu, limp);
         }
         acc.n += __popcll(valid);
@@ -825,8 +1068,8 @@ bcp_kernel(DbDev db, BatchDev b, int warp_bytes, int qcap) {
             b.full_bits[g] = fullm;
         }
         if (b.trail) {
-            b.trail[g * 64 + lane] = ok0 ? (uint16_t)t0 : (uint16_t)0;
-            b.trail[g * 64 + 32 + lane] = ok1 ? (uint16_t)t1 : (uint16_t)0;
+            b.trail[g * 64 + lane] = ok0 ? t0 : 0u;
+            b.trail[g * 64 + 32 + lane] = ok1 ? t1 : 0u;
         }
         if (b.assign) {
             uint64_t* dst = b.assign + g * (uint64_t)db.n_lit;
@@ -858,19 +1101,21 @@ bcp_kernel(DbDev db, BatchDev b, int warp_bytes, int qcap) {
         __syncwarp();
 
         // ---- (5) undo: clear the assumption planes, the implied planes and the queue flags
-        if (!db.unsat) {
+        if (active) {
             for (uint32_t j = lane; j < k; j += 32) {
                 const uint32_t cd = j < 32 ? P_code0 : code[j];
                 if (!(cd & SETCODE_FIXED)) {
-                    c.S[cd] = 0;
-                    c.S[cd ^ 1] = 0;
+                    ulonglong2 z;
+                    z.x = z.y = 0;
+                    *reinterpret_cast<ulonglong2*>(c.S + cd) = z;
                 }
             }
-            for (uint32_t i = lane; i < n_touched; i += 32) {
-                const uint32_t l = c.touched[i];
-                c.S[l] = 0;
-                atomicAnd(&c.inq[l >> 5], ~(1u << (l & 31)));
-                atomicAnd(&c.tset[l >> 5], ~(1u << (l & 31)));
+            if (n_touched) {
+                for (uint32_t i = lane; i < n_touched; i += 32) c.S[c.queue[i]] = 0;
+                for (int i = lane; i < inq_words; i += 32) {
+                    c.inq[i] = 0;
+                    c.tset[i] = 0;
+                }
             }
         }
         __syncwarp();

@@ -28,6 +28,10 @@ static int fail(int code, const std::string& msg) {
             return fail(PDSAT_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
     } while (0)
 
+struct LaunchShape {
+    int stages = 0, stage_bytes = 0, warp_bytes = 0, wpc = 0, smem_bytes = 0, blob_in_smem = 0;
+};
+
 struct pdsat_db {
     HostDb host;
     int device = -1;  // -1: host-only handle (CPU tests of the upload logic)
@@ -36,11 +40,15 @@ struct pdsat_db {
     int sm_count = 0;
     // device copies
     uint4* d_rec = nullptr;
-    uint32_t* d_occ_off = nullptr;
+    unsigned char* d_blob = nullptr;
     uint4* d_occrec = nullptr;
     DbDev dev{};
-    // launch shape
+    // launch shape (per-warp bytes without the words ring, which depends on the batch's set sizes)
     int warps_per_cta = 0, warp_bytes = 0, qcap = 0, smem_bytes = 0, grid = 0;
+    // set_fixed_assumptions renumbers the live variables: batches created before it are stale
+    uint64_t generation = 0;
+    int live_batches = 0;
+    bool zombie = false;  // pdsat_destroy was called while batches were alive
     // mt19937 jump polynomials x^(624*2^t) mod phi resident on the device (lazy)
     uint32_t* d_polys = nullptr;
     int n_polys = 0;
@@ -55,11 +63,13 @@ struct HostPoint {
     std::vector<int32_t> set_vars;
     std::vector<uint32_t> setcode;
     int32_t mode = 0;
-    uint64_t seed = 0, first_sample = 0, n_samples = 0;
+    uint64_t seed = 0, first_sample = 0, n_samples = 0, first_draw = 0;
+    uint32_t kp = 0, flags = 0;
     uint64_t n_groups = 0, group_start = 0, word_off = 0, stream_off = 0, stream_skip = 0, stream_words = 0;
     uint64_t mt_first_round = 0, mt_rounds = 0;
     uint32_t n_assumed_live = 0;
-    std::vector<uint32_t> cand;  // first-wave candidate clauses (first-record ids)
+    std::vector<uint32_t> cand;   // first-wave candidate clauses (first-record ids)
+    std::vector<uint32_t> gcand;  // first-wave candidate gates
     uint32_t cand_off = 0;
     // mt19937 stream segments of 2^mt_m rounds each
     uint32_t mt_index = 0;      // index among the batch's mt19937 points (= state slot of segment 0)
@@ -85,7 +95,7 @@ struct pdsat_batch {
     unsigned long long* d_cost_ext = nullptr;
     uint64_t* d_conflict = nullptr;
     uint64_t* d_full = nullptr;
-    uint16_t* d_trail = nullptr;
+    uint32_t* d_trail = nullptr;
     uint64_t* d_assign = nullptr;
     unsigned long long* d_model_count = nullptr;
     uint32_t* d_model_bits = nullptr;
@@ -114,6 +124,10 @@ struct pdsat_batch {
     int peer_ranks = 0, peer_me = 0;
     uint64_t peer_step = 0;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_h2d = nullptr;  // the last fill's copies out of the pinned staging buffers
+    bool h2d_pending = false;
+    uint64_t generation = 0;       // of the database at creation
+    LaunchShape shape;
     bool filled = false, propagated = false;
     int64_t n_kernels = 0;
     int64_t h2d_bytes_last_fill = 0;
@@ -137,10 +151,10 @@ int pdsat_device_count(int* n) {
 static void free_device_db(pdsat_db* db) {
     if (db->device < 0) return;
     cudaFree(db->d_rec);
-    cudaFree(db->d_occ_off);
+    cudaFree(db->d_blob);
     cudaFree(db->d_occrec);
     db->d_rec = nullptr;
-    db->d_occ_off = nullptr;
+    db->d_blob = nullptr;
     db->d_occrec = nullptr;
 }
 
@@ -150,17 +164,39 @@ static int count_bits_for(int n) {
     return b;
 }
 
+static constexpr int MAX_SMEM = 227 * 1024 - 128;  // the kernel also has a few bytes of static shared memory
+
+// launch shape of bcp_kernel for a batch whose largest set has kp_max (even) words per group
+static LaunchShape launch_shape(const pdsat_db* db, uint32_t kp_max) {
+    LaunchShape L;
+    L.stage_bytes = (int)kp_max * 8;
+    // ~2.25 KB of tiles in flight per warp (x 12..16 warps x 148 SMs covers the HBM latency x
+    // bandwidth product for the small sets); at least double buffering for the large ones
+    int st = 2304 / (L.stage_bytes > 0 ? L.stage_bytes : 16);
+    L.stages = st < 2 ? 2 : (st > 12 ? 12 : st);
+    const int ring = ((L.stages + 1) & ~1) * 8 + L.stages * L.stage_bytes;
+    L.warp_bytes = (db->warp_bytes + ring + 15) & ~15;
+    const int blob = (int)db->host.blob.size();
+    L.blob_in_smem = (blob <= 64 * 1024 && blob + L.warp_bytes <= MAX_SMEM) ? 1 : 0;
+    int wpc = (MAX_SMEM - (L.blob_in_smem ? blob : 0)) / L.warp_bytes;
+    if (wpc > 16) wpc = 16;  // __launch_bounds__(512)
+    L.wpc = wpc;
+    L.smem_bytes = wpc * L.warp_bytes + (L.blob_in_smem ? blob : 0);
+    return L;
+}
+
 // (re)build the device copy + launch shape from db->host
 static int sync_device_db(pdsat_db* db) {
     HostDb& h = db->host;
-    if (2 * (int64_t)h.n_live + 2 >= 0xFFFE)
-        return fail(PDSAT_ERR_LIMIT, "more than 32766 live variables: 16-bit literal codes exhausted");
+    db->generation++;
+    if (2 * (int64_t)h.n_live + 4 >= REC_TAG_MIN)
+        return fail(PDSAT_ERR_LIMIT, "more than 32757 live variables: 16-bit literal codes exhausted");
     if (count_bits_for(h.n_live) > MAX_COUNT_BITS) return fail(PDSAT_ERR_LIMIT, "too many live variables for the counters");
     int n_lit = 2 * h.n_live;
-    int n_planes = n_lit + 2;
+    int n_planes = n_lit + 4;
     int qcap = (n_lit + 2 + 3) & ~3;  // queue ring: one slot per literal
     int inq_words = (n_lit + 31) / 32;
-    int warp_bytes = n_planes * 8 + qcap * 2 + ((n_lit + 2 + 3) & ~3) * 2 + 2 * ((inq_words + 1) & ~1) * 4 + 16;
+    int warp_bytes = n_planes * 8 + qcap * 2 + 2 * ((inq_words + 1) & ~1) * 4 + 16;
     warp_bytes = (warp_bytes + 15) & ~15;
     db->qcap = qcap;
     db->warp_bytes = warp_bytes;
@@ -170,39 +206,36 @@ static int sync_device_db(pdsat_db* db) {
     }
     CU(cudaSetDevice(db->device));
     free_device_db(db);
-    const int max_smem = 227 * 1024 - 64;  // the kernel also has a few bytes of static shared memory
-    // occurrence offsets get one shared-memory copy per CTA if that costs at most one warp
-    const int occ_off_bytes = ((n_lit + 1) * 4 + 15) & ~15;
-    int wpc = max_smem / warp_bytes;
-    int occ_in_smem = 0;
-    if (wpc >= 2 && occ_off_bytes <= warp_bytes) {
-        occ_in_smem = 1;
-        wpc = (max_smem - occ_off_bytes) / warp_bytes;
-    }
-    // wpc == 0: the planes of one 64-sample group do not fit in shared memory with the current
-    // level-0 assignment; evaluation is refused (PDSAT_ERR_LIMIT) until fixed assumptions
-    // shrink the live set
-    if (wpc > 16) wpc = 16;  // __launch_bounds__(512)
-    db->warps_per_cta = wpc;
-    db->smem_bytes = wpc * warp_bytes + (occ_in_smem ? occ_off_bytes : 0);
+    // shape for a small set, reported by pdsat_db_get_info; wpc == 0: the planes of one
+    // 64-sample group do not fit in shared memory with the current level-0 assignment;
+    // evaluation is refused (PDSAT_ERR_LIMIT) until fixed assumptions shrink the live set
+    const LaunchShape L = launch_shape(db, 32);
+    db->warps_per_cta = L.wpc;
+    db->smem_bytes = L.smem_bytes;
     db->grid = db->sm_count;
     size_t nrec = (size_t)h.n_rec;
     CU(cudaMalloc(&db->d_rec, (nrec ? nrec : 1) * sizeof(uint4)));
-    CU(cudaMalloc(&db->d_occ_off, h.occ_off.size() * sizeof(uint32_t)));
+    CU(cudaMalloc(&db->d_blob, h.blob.size()));
     CU(cudaMalloc(&db->d_occrec, (h.occ.size() ? h.occ.size() : 1) * sizeof(uint4)));
     if (nrec) CU(cudaMemcpy(db->d_rec, h.rec.data(), nrec * sizeof(uint4), cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(db->d_occ_off, h.occ_off.data(), h.occ_off.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(db->d_blob, h.blob.data(), h.blob.size(), cudaMemcpyHostToDevice));
     if (!h.occ.empty())
         CU(cudaMemcpy(db->d_occrec, h.occrec.data(), h.occ.size() * sizeof(uint4), cudaMemcpyHostToDevice));
     db->dev.rec = db->d_rec;
-    db->dev.occ_off = db->d_occ_off;
     db->dev.occrec = db->d_occrec;
-    db->dev.occ_off_in_smem = occ_in_smem;
+    db->dev.blob = db->d_blob;
+    db->dev.blob_bytes = (uint32_t)h.blob.size();
+    db->dev.off_gocc_off = h.blob_gocc_off;
+    db->dev.off_gocc = h.blob_gocc;
+    db->dev.off_grec = h.blob_grec;
+    db->dev.blob_in_smem = L.blob_in_smem;
     db->dev.n_live = h.n_live;
     db->dev.n_lit = n_lit;
     db->dev.n_base_assigned = h.n_base_assigned;
     db->dev.unsat = h.base_ok ? 0 : 1;
-    CU(cudaFuncSetAttribute(bcp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    db->dev.n_gates = (int32_t)h.gates.size();
+    db->dev.n_rec = (int32_t)h.n_rec;
+    CU(cudaFuncSetAttribute(bcp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM));
     return PDSAT_OK;
 }
 
@@ -266,14 +299,39 @@ int pdsat_db_get_info(const pdsat_db* db, pdsat_db_info* info) {
     info->warps_per_cta = db->warps_per_cta;
     info->smem_bytes = db->smem_bytes;
     info->grid = db->grid;
-    info->db_in_smem = db->dev.occ_off_in_smem;
+    info->db_in_smem = db->dev.blob_in_smem;
     info->sm_count = db->sm_count;
+    info->n_gates = (int32_t)h.gates.size();
+    info->blob_bytes = (int32_t)h.blob.size();
+    info->n_gate_clauses = h.n_gate_clauses;
     return PDSAT_OK;
 }
 
 int pdsat_db_base_assignment(const pdsat_db* db, uint8_t* assigns) {
     if (!db || !assigns) return fail(PDSAT_ERR_ARG, "pdsat_db_base_assignment: bad argument");
     memcpy(assigns, db->host.base_assign.data(), (size_t)db->host.n_vars);
+    return PDSAT_OK;
+}
+
+int pdsat_db_gates(const pdsat_db* db, int32_t cap, pdsat_gate* out, int32_t* n_gates) {
+    if (!db || !n_gates) return fail(PDSAT_ERR_ARG, "pdsat_db_gates: bad argument");
+    const HostDb& h = db->host;
+    *n_gates = (int32_t)h.gates.size();
+    for (int32_t g = 0; out && g < cap && g < (int32_t)h.gates.size(); g++) {
+        const HostGate& hg = h.gates[g];
+        pdsat_gate& o = out[g];
+        memset(&o, 0, sizeof(o));
+        o.type = hg.type;
+        o.parity = hg.parity;
+        o.m = hg.m;
+        o.n_clauses = (int32_t)hg.n_clauses;
+        for (int i = 0; i < hg.m; i++) o.x[i] = h.var_of_live[hg.x[i]] + 1;
+        o.lb = o.lc = -1;
+        if (hg.type == 1) {
+            o.lb = 2 * h.var_of_live[hg.lb >> 1] + (hg.lb & 1);
+            o.lc = 2 * h.var_of_live[hg.lc >> 1] + (hg.lc & 1);
+        }
+    }
     return PDSAT_OK;
 }
 
@@ -296,6 +354,10 @@ int pdsat_set_stream(pdsat_db* db, void* cuda_stream) {
 
 void pdsat_destroy(pdsat_db* db) {
     if (!db) return;
+    if (db->live_batches > 0) {  // released by the last pdsat_batch_destroy
+        db->zombie = true;
+        return;
+    }
     if (db->device >= 0) {
         cudaSetDevice(db->device);
         free_device_db(db);
@@ -315,7 +377,7 @@ static int need_device(const pdsat_db* db) {
 // position of a point's sample window inside its mt19937 stream
 static void mt_plan(HostPoint& hp) {
     const uint64_t k = hp.set_vars.size();
-    const uint64_t d0 = hp.first_sample * k;
+    const uint64_t d0 = hp.first_draw + hp.first_sample * k;
     hp.mt_first_round = d0 / 624;
     hp.stream_skip = d0 - hp.mt_first_round * 624;
     // rounds to allocate: worst-case skip (623), so that a reseed never needs more
@@ -340,6 +402,8 @@ int pdsat_batch_create(pdsat_db* db, int32_t n_points, const pdsat_point* points
     const HostDb& h = db->host;
     pdsat_batch* b = new pdsat_batch();
     b->db = db;
+    b->generation = db->generation;
+    db->live_batches++;
     b->out_flags = out_flags;
     b->max_models = max_models < 0 ? 0 : max_models;
     b->model_words = (h.n_live + 31) / 32;
@@ -350,13 +414,15 @@ int pdsat_batch_create(pdsat_db* db, int32_t n_points, const pdsat_point* points
     std::vector<uint8_t> seen((size_t)h.n_vars);
     std::vector<uint16_t> in_set_count((size_t)h.n_rec + 1, 0);
     std::vector<uint32_t> touched_rec;
+    std::vector<uint8_t> live_in_set((size_t)h.n_live + 1, 0), gate_seen(h.gates.size() + 1, 0);
+    uint32_t kp_max = 2;
     for (int p = 0; p < n_points; p++) {
         const pdsat_point& in = points[p];
         HostPoint& hp = b->pts[p];
         if (in.k <= 0 || !in.set_vars || in.n_samples == 0 || in.mode < 0 || in.mode > 3 ||
             (in.mode == PDSAT_MODE_EXPLICIT && !in.explicit_values) ||
             (in.mode == PDSAT_MODE_RANDOM_COUNTER && (in.first_sample & 63))) {
-            delete b;
+            pdsat_batch_destroy(b);
             return fail(PDSAT_ERR_ARG, "pdsat_batch_create: bad point " + std::to_string(p));
         }
         std::fill(seen.begin(), seen.end(), 0);
@@ -366,12 +432,13 @@ int pdsat_batch_create(pdsat_db* db, int32_t n_points, const pdsat_point* points
         for (int j = 0; j < in.k; j++) {
             int32_t v = in.set_vars[j] - 1;
             if (v < 0 || v >= h.n_vars || seen[v]) {
-                delete b;
+                pdsat_batch_destroy(b);
                 return fail(PDSAT_ERR_ARG, "pdsat_batch_create: set variable out of range or repeated");
             }
             seen[v] = 1;
             if (h.live_of_var[v] < 0) {
                 hp.setcode[j] = SETCODE_FIXED | (uint32_t)(h.base_assign[v] & 1);
+                hp.flags |= POINT_HAS_FIXED;
             } else {
                 hp.setcode[j] = (uint32_t)(2 * h.live_of_var[v]);
                 hp.n_assumed_live++;
@@ -396,18 +463,51 @@ int pdsat_batch_create(pdsat_db* db, int32_t n_points, const pdsat_point* points
                 in_set_count[r] = 0;
             }
             std::sort(hp.cand.begin(), hp.cand.end());
+            // gates: one that has two unknown members cannot imply or conflict.  Members are the
+            // xor variables and, for ANDXOR, the product Lb & Lc (possibly known as soon as one
+            // of its literals is in the set)
+            if (!h.gates.empty()) {
+                for (int j = 0; j < in.k; j++) {
+                    const int32_t lv = h.live_of_var[in.set_vars[j] - 1];
+                    if (lv >= 0) live_in_set[lv] = 1;
+                }
+                for (int j = 0; j < in.k; j++) {
+                    const int32_t lv = h.live_of_var[in.set_vars[j] - 1];
+                    if (lv < 0) continue;
+                    for (uint32_t o = h.gocc_off[lv]; o < h.gocc_off[lv + 1]; o++) {
+                        const uint32_t g = h.gocc[o];
+                        if (gate_seen[g]) continue;
+                        gate_seen[g] = 1;
+                        const HostGate& hg = h.gates[g];
+                        int outside = 0;
+                        for (int i = 0; i < hg.m; i++) outside += live_in_set[hg.x[i]] ? 0 : 1;
+                        if (hg.type == 1 && !live_in_set[hg.lb >> 1] && !live_in_set[hg.lc >> 1]) outside++;
+                        if (outside <= 1) hp.gcand.push_back(g);
+                    }
+                }
+                for (int j = 0; j < in.k; j++) {
+                    const int32_t lv = h.live_of_var[in.set_vars[j] - 1];
+                    if (lv < 0) continue;
+                    live_in_set[lv] = 0;
+                    for (uint32_t o = h.gocc_off[lv]; o < h.gocc_off[lv + 1]; o++) gate_seen[h.gocc[o]] = 0;
+                }
+                std::sort(hp.gcand.begin(), hp.gcand.end());
+            }
         }
         hp.cand_off = (uint32_t)n_cand;
-        n_cand += hp.cand.size();
+        n_cand += hp.cand.size() + hp.gcand.size();
         hp.mode = in.mode;
         hp.seed = in.seed;
         hp.first_sample = in.first_sample;
+        hp.first_draw = in.mode == PDSAT_MODE_RANDOM_MT19937 ? in.first_draw : 0;
         hp.n_samples = in.n_samples;
         hp.n_groups = (in.n_samples + 63) / 64;
         hp.group_start = groups;
         hp.word_off = words;
+        hp.kp = ((uint32_t)in.k + 1u) & ~1u;  // 16-byte tiles for the bulk copies
+        if (hp.kp > kp_max) kp_max = hp.kp;
         groups += hp.n_groups;
-        words += hp.n_groups * (uint64_t)in.k;
+        words += hp.n_groups * (uint64_t)hp.kp;
         if (in.mode == PDSAT_MODE_RANDOM_MT19937) {
             mt_plan(hp);
             hp.mt_index = (uint32_t)b->n_mt_points++;
@@ -447,6 +547,11 @@ int pdsat_batch_create(pdsat_db* db, int32_t n_points, const pdsat_point* points
     }
     b->n_groups = groups;
     b->n_words = words;
+    b->shape = launch_shape(db, kp_max);
+    if (b->shape.wpc < 1) {
+        pdsat_batch_destroy(b);
+        return fail(PDSAT_ERR_LIMIT, "assignment state + word tiles of one sample group exceed shared memory");
+    }
 
     auto bail = [&](int code, const std::string& m) {
         pdsat_batch_destroy(b);
@@ -475,7 +580,7 @@ int pdsat_batch_create(pdsat_db* db, int32_t n_points, const pdsat_point* points
         CUB(cudaMalloc(&b->d_conflict, sizeof(uint64_t) * groups));
         CUB(cudaMalloc(&b->d_full, sizeof(uint64_t) * groups));
     }
-    if (out_flags & PDSAT_OUT_TRAIL) CUB(cudaMalloc(&b->d_trail, sizeof(uint16_t) * 64 * groups));
+    if (out_flags & PDSAT_OUT_TRAIL) CUB(cudaMalloc(&b->d_trail, sizeof(uint32_t) * 64 * groups));
     if (out_flags & PDSAT_OUT_ASSIGN)
         CUB(cudaMalloc(&b->d_assign, sizeof(uint64_t) * groups * (size_t)(h.n_live > 0 ? 2 * h.n_live : 1)));
     if (b->n_mt_segs) {
@@ -531,28 +636,43 @@ int pdsat_batch_create(pdsat_db* db, int32_t n_points, const pdsat_point* points
             pd.mode = (uint32_t)hp.mode;
             pd.n_assumed_live = hp.n_assumed_live;
             pd.cand_off = hp.cand_off;
-            pd.cand_cnt = (uint32_t)hp.cand.size();
+            pd.cand_cnt = (uint32_t)(hp.cand.size() + hp.gcand.size());
+            pd.kp = hp.kp;
+            pd.flags = hp.flags;
             off += pd.k;
             codes.insert(codes.end(), hp.setcode.begin(), hp.setcode.end());
-            if (!hp.cand.empty()) {
-                std::vector<uint16_t> recs(hp.cand.size() * REC_SLOTS);
-                for (size_t i = 0; i < hp.cand.size(); i++) h.inline_record(hp.cand[i], &recs[i * REC_SLOTS]);
-                CUB(cudaMemcpy(b->d_cand + hp.cand_off, recs.data(), sizeof(uint4) * hp.cand.size(), cudaMemcpyHostToDevice));
+            if (pd.cand_cnt) {  // gates first, then clauses: neighbouring lanes take the same path
+                std::vector<uint16_t> recs((size_t)pd.cand_cnt * REC_SLOTS);
+                size_t i = 0;
+                for (uint32_t g : hp.gcand) memcpy(&recs[i++ * REC_SLOTS], &h.gate_rec[(size_t)g * REC_SLOTS], sizeof(uint16_t) * REC_SLOTS);
+                for (uint32_t r : hp.cand) h.inline_record(r, &recs[i++ * REC_SLOTS]);
+                CUB(cudaMemcpy(b->d_cand + hp.cand_off, recs.data(), sizeof(uint4) * pd.cand_cnt, cudaMemcpyHostToDevice));
             }
         }
         CUB(cudaMemcpy(b->d_setcode, codes.data(), sizeof(uint32_t) * n_codes, cudaMemcpyHostToDevice));
         CUB(cudaMemcpy(b->d_points, b->h_points, sizeof(PointDev) * n_points, cudaMemcpyHostToDevice));
     }
     for (int i = 0; i < 4; i++) CUB(cudaEventCreate(&b->ev[i]));
+    CUB(cudaEventCreateWithFlags(&b->ev_h2d, cudaEventDisableTiming));
 #undef CUB
     *out = b;
     return PDSAT_OK;
+}
+
+// the pinned staging buffers (h_points, h_mt_*) may still be read by the previous fill's
+// asynchronous copies: wait for them before the host rewrites the buffers
+static void staging_wait(pdsat_batch* b) {
+    if (b->h2d_pending) {
+        cudaEventSynchronize(b->ev_h2d);
+        b->h2d_pending = false;
+    }
 }
 
 int pdsat_batch_reseed(pdsat_batch* b, int32_t point, uint64_t seed, uint64_t first_sample) {
     if (!b || point < 0 || point >= (int)b->pts.size()) return fail(PDSAT_ERR_ARG, "pdsat_batch_reseed: bad argument");
     HostPoint& hp = b->pts[point];
     if (hp.mode == PDSAT_MODE_EXPLICIT) return fail(PDSAT_ERR_ARG, "pdsat_batch_reseed: explicit point");
+    staging_wait(b);
     if (hp.mode == PDSAT_MODE_RANDOM_COUNTER && (first_sample & 63))
         return fail(PDSAT_ERR_ARG, "pdsat_batch_reseed: first_sample must be a multiple of 64");
     hp.seed = seed;
@@ -570,10 +690,30 @@ int pdsat_batch_reseed(pdsat_batch* b, int32_t point, uint64_t seed, uint64_t fi
     return PDSAT_OK;
 }
 
+int pdsat_batch_set_first_draw(pdsat_batch* b, int32_t point, uint64_t first_draw) {
+    if (!b || point < 0 || point >= (int)b->pts.size()) return fail(PDSAT_ERR_ARG, "pdsat_batch_set_first_draw: bad argument");
+    HostPoint& hp = b->pts[point];
+    if (hp.mode != PDSAT_MODE_RANDOM_MT19937) return fail(PDSAT_ERR_ARG, "pdsat_batch_set_first_draw: not a mt19937 point");
+    staging_wait(b);
+    hp.first_draw = first_draw;
+    mt_plan(hp);
+    b->h_points[point].stream_skip = hp.stream_skip;
+    b->filled = false;
+    return PDSAT_OK;
+}
+
+static int stale(const pdsat_batch* b) {
+    if (b->generation != b->db->generation)
+        return fail(PDSAT_ERR_ARG, "stale batch: pdsat_set_fixed_assumptions rebuilt the database after this batch was created");
+    return PDSAT_OK;
+}
+
 int pdsat_batch_fill(pdsat_batch* b) {
     if (!b) return fail(PDSAT_ERR_ARG, "pdsat_batch_fill: null batch");
+    if (stale(b)) return PDSAT_ERR_ARG;
     pdsat_db* db = b->db;
     CU(cudaSetDevice(db->device));
+    staging_wait(b);  // the previous fill may still be reading the pinned staging buffers
     cudaStream_t st = db->stream;
     CU(cudaEventRecord(b->ev[0], st));
     CU(cudaMemcpyAsync(b->d_points, b->h_points, sizeof(PointDev) * b->pts.size(), cudaMemcpyHostToDevice, st));
@@ -689,6 +829,8 @@ int pdsat_batch_fill(pdsat_batch* b) {
             h2d += (int64_t)(sizeof(uint32_t) * hp.stream_words);
         }
     }
+    CU(cudaEventRecord(b->ev_h2d, st));
+    b->h2d_pending = true;
     BatchDev bd{};
     bd.points = b->d_points;
     bd.n_points = (int32_t)b->pts.size();
@@ -710,6 +852,7 @@ int pdsat_batch_fill(pdsat_batch* b) {
 int pdsat_batch_propagate(pdsat_batch* b) {
     if (!b) return fail(PDSAT_ERR_ARG, "pdsat_batch_propagate: null batch");
     if (!b->filled) return fail(PDSAT_ERR_ARG, "pdsat_batch_propagate: batch not filled");
+    if (stale(b)) return PDSAT_ERR_ARG;
     pdsat_db* db = b->db;
     CU(cudaSetDevice(db->device));
     cudaStream_t st = db->stream;
@@ -737,7 +880,12 @@ int pdsat_batch_propagate(pdsat_batch* b) {
     bd.model_sample = b->d_model_sample;
     bd.max_models = b->max_models;
     bd.model_words = b->model_words;
-    uint64_t ctas_needed = (b->n_groups + db->warps_per_cta - 1) / db->warps_per_cta;
+    const LaunchShape& L = b->shape;
+    bd.ring_stages = L.stages;
+    bd.ring_stage_bytes = L.stage_bytes;
+    DbDev dev = db->dev;
+    dev.blob_in_smem = L.blob_in_smem;
+    uint64_t ctas_needed = (b->n_groups + L.wpc - 1) / L.wpc;
     int grid = (int)(ctas_needed < (uint64_t)db->grid ? ctas_needed : (uint64_t)db->grid);
     if (grid < 1) grid = 1;
     const int n_cost_words = PDSAT_COST_WORDS * (int)b->pts.size();
@@ -750,7 +898,7 @@ int pdsat_batch_propagate(pdsat_batch* b) {
         bd.peer.parity = parity;
         bd.peer.n_words = n_cost_words;
     }
-    bcp_kernel<<<grid, db->warps_per_cta * 32, db->smem_bytes, st>>>(db->dev, bd, db->warp_bytes, db->qcap);
+    bcp_kernel<<<grid, L.wpc * 32, L.smem_bytes, st>>>(dev, bd, L.warp_bytes, db->qcap);
     b->n_kernels++;
     if (b->peer_ranks > 0) {
         const unsigned long long target = (unsigned long long)(b->peer_step / 2 + 1) * b->peer_ranks;
@@ -830,12 +978,12 @@ int pdsat_batch_flags(pdsat_batch* b, int32_t point, uint64_t* conflict_bits, ui
     return PDSAT_OK;
 }
 
-int pdsat_batch_trail(pdsat_batch* b, int32_t point, uint16_t* trail) {
+int pdsat_batch_trail(pdsat_batch* b, int32_t point, uint32_t* trail) {
     if (!b || !trail || point < 0 || point >= (int)b->pts.size()) return fail(PDSAT_ERR_ARG, "pdsat_batch_trail: bad argument");
     if (!b->d_trail || !b->propagated) return fail(PDSAT_ERR_ARG, "pdsat_batch_trail: PDSAT_OUT_TRAIL not requested / not run");
     const HostPoint& hp = b->pts[point];
     CU(cudaStreamSynchronize(b->db->stream));
-    CU(cudaMemcpy(trail, b->d_trail + hp.group_start * 64, sizeof(uint16_t) * hp.n_samples, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(trail, b->d_trail + hp.group_start * 64, sizeof(uint32_t) * hp.n_samples, cudaMemcpyDeviceToHost));
     return PDSAT_OK;
 }
 
@@ -981,7 +1129,13 @@ void pdsat_batch_destroy(pdsat_batch* b) {
     if (b->h_points) cudaFreeHost(b->h_points);
     for (int i = 0; i < 4; i++)
         if (b->ev[i]) cudaEventDestroy(b->ev[i]);
+    if (b->ev_h2d) cudaEventDestroy(b->ev_h2d);
+    pdsat_db* db = b->db;
     delete b;
+    if (db && --db->live_batches == 0 && db->zombie) {
+        db->zombie = false;
+        pdsat_destroy(db);
+    }
 }
 
 int pdsat_eval_batch(pdsat_db* db, int32_t n_points, const pdsat_point* points, pdsat_cost* costs) {
