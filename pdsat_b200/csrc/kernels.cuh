@@ -439,19 +439,18 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // Per-warp working set in shared memory (one warp owns one group of 64 samples):
 //   S[l]      64-bit plane per literal: samples in which literal l is TRUE.  S[2v], S[2v+1] (the
 //             TRUE and FALSE plane of variable v) are adjacent: one 16-byte load fetches both
-//   queue     ring of implied literals whose occurrence lists still have to be visited; after the
-//             fixpoint the same array holds the compacted list of implied literals (undo list)
-//   inq       bitset "literal is in the queue";  tset  bitset "literal was implied in this group"
+//   fill      bitset: literals that gained samples since they were last visited - the frontier
+//             under construction (making a literal true = atomicOr on its plane + one atomicOr here)
+//   drain     bitset: the frontier being visited (the two swap roles at every level: the
+//             propagation is level-synchronous, breadth first)
+//   tset      bitset: literals implied in this group (undo list, per-sample trail counts)
 //   ring      multi-stage ring of assumption-word tiles filled by bulk async copies
 struct WarpCtx {
     uint64_t* S;
-    uint16_t* queue;
-    uint32_t* inq;
+    uint32_t* fill;
+    uint32_t* drain;
     uint32_t* tset;
-    uint64_t* dead;     // samples in conflict
-    uint32_t* qtail;
-    uint32_t* ntouched;
-    uint32_t qcap, qmagic;  // ring size (one slot per literal) and ceil(2^32 / qcap)
+    uint64_t* dead;  // samples in conflict
 };
 
 // 64-bit OR into shared memory as two native 32-bit ATOMS.OR (a 64-bit shared atomicOr
@@ -465,32 +464,25 @@ __device__ __forceinline__ uint64_t or64_shared(uint64_t* p, uint64_t v) {
     return ((uint64_t)ohi << 32) | olo;
 }
 
-// pos mod qcap without a division (pos stays far below 2^32)
-__device__ __forceinline__ uint32_t ring_index(const WarpCtx& c, uint32_t pos) {
-    int32_t r = (int32_t)(pos - __umulhi(pos, c.qmagic) * c.qcap);
-    if (r < 0) r += (int32_t)c.qcap;
-    return (uint32_t)r;
-}
-
-__device__ __forceinline__ void push_lit(const WarpCtx& c, uint32_t l) {
-    const uint32_t bit = 1u << (l & 31);
-    const uint32_t old = atomicOr(&c.inq[l >> 5], bit);
-    if (!(old & bit)) {
-        const uint32_t pos = atomicAdd(c.qtail, 1u);
-        c.queue[ring_index(c, pos)] = (uint16_t)l;
-    }
-}
-
 // make literal l true in the samples `bits` (Solver.cc:579-585 uncheckedEnqueue, for up to 64
-// samples at once).  Planes only gain bits; a literal that gained a bit is logged once per group
-// and (re)queued, so every clause / gate that can react to it is visited again.
+// samples at once).  Planes only gain bits; a literal that gained a bit joins the next frontier,
+// so every clause / gate that can react to it is visited (again).
 __device__ __forceinline__ void set_true(const WarpCtx& c, uint32_t l, uint64_t bits) {
     const uint64_t old = or64_shared(&c.S[l], bits);
-    if (bits & ~old) {
-        const uint32_t bit = 1u << (l & 31);
-        if (!(atomicOr(&c.tset[l >> 5], bit) & bit)) atomicAdd(c.ntouched, 1u);
-        push_lit(c, l);
-    }
+    if (bits & ~old) atomicOr(&c.fill[l >> 5], 1u << (l & 31));
+}
+
+// variable with TRUE-plane code tcode (even): true in the samples t, false in the samples f
+__device__ __forceinline__ void set_pair(const WarpCtx& c, uint32_t tcode, uint64_t t, uint64_t f) {
+    uint32_t* q = reinterpret_cast<uint32_t*>(c.S + tcode);  // T.lo T.hi F.lo F.hi
+    const uint32_t tl = (uint32_t)t, th = (uint32_t)(t >> 32), fl = (uint32_t)f, fh = (uint32_t)(f >> 32);
+    uint32_t nt = 0, nf = 0;
+    if (tl) nt |= tl & ~atomicOr(q, tl);
+    if (th) nt |= th & ~atomicOr(q + 1, th);
+    if (fl) nf |= fl & ~atomicOr(q + 2, fl);
+    if (fh) nf |= fh & ~atomicOr(q + 3, fh);
+    const uint32_t m = (nt ? 1u : 0u) | (nf ? 2u : 0u);
+    if (m) atomicOr(&c.fill[tcode >> 5], m << (tcode & 31));  // both literals sit in one word
 }
 
 __device__ __forceinline__ uint32_t rec_slot(const uint4& r, int j) {
@@ -577,28 +569,27 @@ __device__ __forceinline__ void eval_clause(const uint4& r0, const uint4* __rest
 
 // Gate in closed form on 64 samples.  XOR: x_0 ^ ... ^ x_6 = p.  ANDXOR: x_0 ^ ... ^ x_4 ^ q = p
 // with q = Lb & Lc (q is known 1 where both literals are true, known 0 where one is false).
-// With u_i = "x_i unknown":  conflict where nothing is unknown and the parity is wrong; where
-// exactly one member is unknown it takes the value  p ^ xor(known values).  For the product: q
-// must be 1 -> Lb and Lc become true; q must be 0 and one literal is true -> the other becomes
-// false.  Equal to unit propagation over the gate's clauses (tests/test_gates.py).
+// Members = the xor variables (and q).  Conflict where no member is unknown and the parity is
+// wrong; where exactly one member is unknown it takes the value  p ^ xor(known values).  For the
+// product: q must be 1 -> Lb and Lc become true; q must be 0 and one literal is true -> the
+// other becomes false.  Equal to unit propagation over the gate's clauses (tests/test_gates.py).
+// The two kinds share one instruction stream (selects on the kind mask), so a warp that mixes
+// them does not diverge until something is actually implied.
 __device__ __forceinline__ void imply_var(const WarpCtx& c, uint32_t tcode, uint64_t imp, uint64_t par) {
-    if (imp) {
-        const uint64_t t = imp & par, f = imp & ~par;
-        if (t) set_true(c, tcode, t);
-        if (f) set_true(c, tcode + 1u, f);
-    }
+    if (imp) set_pair(c, tcode, imp & par, imp & ~par);
 }
 
 __device__ __forceinline__ void eval_gate(const uint4& r, const WarpCtx& c, uint64_t live) {
     const uint32_t tag = r.w >> 16;
-    const bool andxor = tag >= REC_GATE_ANDXOR_D;
-    uint64_t par = (tag & 1u) ? ~0ull : 0ull;  // p ^ xor(values): must end up 0
-    uint64_t any = 0, two = 0;
-    uint64_t u0, u1, u2, u3, u4, u5 = 0, u6 = 0, tb = 0, tc = 0, qu = 0;
+    const uint64_t am = (tag & 2u) ? ~0ull : 0ull;  // ANDXOR
+    uint64_t par = (tag & 1u) ? ~0ull : 0ull;       // p ^ xor(values): must end up 0
+    uint64_t any = 0, two = 0, both = 0;
+    uint64_t u0, u1, u2, u3, u4;
     uint64_t t, f;
 #define PDSAT_XVAR(U, CODE)              \
     ld_pair(c.S, (CODE), t, f);          \
     U = ~(t | f);                        \
+    both |= t & f;                       \
     par ^= t;                            \
     two |= any & U;                      \
     any |= U;
@@ -607,26 +598,27 @@ __device__ __forceinline__ void eval_gate(const uint4& r, const WarpCtx& c, uint
     PDSAT_XVAR(u2, r.y & 0xFFFFu)
     PDSAT_XVAR(u3, r.y >> 16)
     PDSAT_XVAR(u4, r.z & 0xFFFFu)
-    const uint32_t c5 = r.z >> 16, c6 = r.w & 0xFFFFu;
-    if (!andxor) {
-        PDSAT_XVAR(u5, c5)
-        PDSAT_XVAR(u6, c6)
-    } else {
-        uint64_t e, o;
-        ld_pair(c.S, c5, e, o);
-        tb = (c5 & 1u) ? o : e;
-        const uint64_t fb = (c5 & 1u) ? e : o;
-        ld_pair(c.S, c6, e, o);
-        tc = (c6 & 1u) ? o : e;
-        const uint64_t fc = (c6 & 1u) ? e : o;
-        const uint64_t q1 = tb & tc, q0 = fb | fc;
-        qu = ~(q1 | q0);
-        par ^= q1;
-        two |= any & qu;
-        any |= qu;
-    }
 #undef PDSAT_XVAR
-    const uint64_t confl = ~any & par & live;
+    // slots 5, 6: two more xor variables (TRUE-plane codes, even) or the literals Lb, Lc
+    const uint32_t c5 = r.z >> 16, c6 = r.w & 0xFFFFu;
+    uint64_t e, o;
+    ld_pair(c.S, c5, e, o);
+    const uint64_t tb = (c5 & 1u) ? o : e, fb = (c5 & 1u) ? e : o;
+    ld_pair(c.S, c6, e, o);
+    const uint64_t tc = (c6 & 1u) ? o : e, fc = (c6 & 1u) ? e : o;
+    const uint64_t q1 = tb & tc;
+    const uint64_t m5 = (~(tb | fb) & ~am) | (~(q1 | fb | fc) & am);  // x5 unknown / q unknown
+    const uint64_t m6 = ~(tc | fc) & ~am;                              // x6 unknown / -
+    par ^= ((tb ^ tc) & ~am) | (q1 & am);
+    two |= any & m5;
+    any |= m5;
+    two |= any & m6;
+    any |= m6;
+    // a member that two reasons made true AND false: the later reason's clause is falsified.
+    // (Clauses notice this by themselves - all their literals are false; two gates that read the
+    // variable through opposite polarities would each see a consistent value.)
+    both |= (tb & fb) | (tc & fc);
+    const uint64_t confl = ((~any & par) | both) & live;
     const uint64_t one = any & ~two & live;
     if (confl) or64_shared(c.dead, confl);
     if (one) {
@@ -635,17 +627,16 @@ __device__ __forceinline__ void eval_gate(const uint4& r, const WarpCtx& c, uint
         imply_var(c, r.y & 0xFFFFu, one & u2, par);
         imply_var(c, r.y >> 16, one & u3, par);
         imply_var(c, r.z & 0xFFFFu, one & u4, par);
-        if (!andxor) {
-            imply_var(c, c5, one & u5, par);
-            imply_var(c, c6, one & u6, par);
-        } else {
-            const uint64_t iq = one & qu;
-            if (iq) {
-                const uint64_t s1 = iq & par, s0 = iq & ~par;
-                if (s1 & ~tb) set_true(c, c5, s1 & ~tb);
-                if (s1 & ~tc) set_true(c, c6, s1 & ~tc);
-                if (s0 & tb) set_true(c, c6 ^ 1u, s0 & tb);
-                if (s0 & tc) set_true(c, c5 ^ 1u, s0 & tc);
+        const uint64_t i5 = one & m5, i6 = one & m6;
+        if (i5 | i6) {
+            if (!am) {
+                imply_var(c, c5, i5, par);
+                imply_var(c, c6, i6, par);
+            } else {
+                const uint64_t s1 = i5 & par, s0 = i5 & ~par;
+                const uint64_t b_true = s1 & ~tb, b_false = s0 & tc, c_true = s1 & ~tc, c_false = s0 & tb;
+                if (b_true | b_false) set_pair(c, c5 & ~1u, (c5 & 1u) ? b_false : b_true, (c5 & 1u) ? b_true : b_false);
+                if (c_true | c_false) set_pair(c, c6 & ~1u, (c6 & 1u) ? c_false : c_true, (c6 & 1u) ? c_true : c_false);
             }
         }
     }
@@ -673,7 +664,6 @@ __device__ __forceinline__ uint64_t warp_sum64(uint64_t v) {
 }
 
 static constexpr int MAX_COUNT_BITS = 15;
-static constexpr int MULTI_POP = 32;  // queued literals processed per propagation round (one per lane)
 
 struct WarpAcc {
     uint64_t n, n_conflict, n_full, sum, sumsq, n_impl, pops, touched;
@@ -695,8 +685,8 @@ __device__ __forceinline__ void flush_acc(WarpAcc& a, unsigned long long* cost, 
     a.n = a.n_conflict = a.n_full = a.sum = a.sumsq = a.n_impl = a.pops = a.touched = 0;
 }
 
-// owner of flattened item i among the first MULTI_POP lanes' lists: the smallest q with
-// cum[q] > i (cum = inclusive prefix sums held one per lane)
+// owner of flattened item i among the lanes' lists: the smallest q with cum[q] > i (cum =
+// inclusive prefix sums held one per lane)
 __device__ __forceinline__ int find_owner(uint32_t cum, uint32_t i) {
     int lo = 0;
 #pragma unroll
@@ -716,21 +706,27 @@ __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
     return v;
 }
 
-// per-sample count of set planes among the literals list[0..n): bit-sliced vertical counters of
-// NB bits (n < 2^NB), summed over the lanes; returns the counts of samples lane and lane + 32
+// per-sample count of set planes among the literals of the bitset `set`: bit-sliced vertical
+// counters of NB bits (count < 2^NB) per lane over the words the lane owns, then summed over
+// the lanes; returns the counts of samples lane and lane + 32
 template <int NB>
-__device__ __forceinline__ void count_planes(const uint64_t* S, const uint16_t* list, uint32_t n, int lane,
+__device__ __forceinline__ void count_planes(const uint64_t* S, const uint32_t* set, int n_words, int lane,
                                              uint32_t& cnt0, uint32_t& cnt1) {
     uint64_t cb[NB];
 #pragma unroll
     for (int q = 0; q < NB; q++) cb[q] = 0;
-    for (uint32_t i = lane; i < n; i += 32) {
-        uint64_t carry = S[list[i]];
+    for (int w = lane; w < n_words; w += 32) {
+        uint32_t bits = set[w];
+        while (bits) {
+            const int bp = __ffs(bits) - 1;
+            bits &= bits - 1;
+            uint64_t carry = S[32 * w + bp];
 #pragma unroll
-        for (int q = 0; q < NB; q++) {
-            const uint64_t t = cb[q] & carry;
-            cb[q] ^= carry;
-            carry = t;
+            for (int q = 0; q < NB; q++) {
+                const uint64_t t = cb[q] & carry;
+                cb[q] ^= carry;
+                carry = t;
+            }
         }
     }
 #pragma unroll
@@ -760,14 +756,14 @@ __device__ __forceinline__ void count_planes(const uint64_t* S, const uint16_t* 
 // of the next `stages` groups are in flight behind the propagation);  (1) write the assumption
 // planes;  (2) FIRST WAVE: visit the point's candidate records - the only clauses / gates that
 // can be unit or falsified when just the set variables are assigned (computed once per point on
-// the host; MiniSat gets the same effect lazily from its two watched literals);  (3) drain the
-// queue of implied literals, visiting every gate that contains the variable and every clause that
-// contains the complement of a literal that became true (Solver.cc:611-655);  (4) per-sample
-// results and integer cost accumulation;  (5) undo: clear only the planes that were written.
+// the host; MiniSat gets the same effect lazily from its two watched literals);  (3) visit the
+// frontier level by level: every gate that contains the variable and every clause that contains
+// the complement of a literal that gained samples (Solver.cc:611-655), until nothing changes;
+// (4) per-sample results and integer cost accumulation;  (5) undo: clear only the planes written.
 // A point without candidates and without level-0-fixed set variables cannot start BCP at all:
 // its groups skip (1), (2), (3) and (5) - the words still stream through the ring.
 __global__ void __launch_bounds__(512, 1)
-bcp_kernel(DbDev db, BatchDev b, int warp_bytes, int qcap) {
+bcp_kernel(DbDev db, BatchDev b, int warp_bytes) {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ __align__(8) uint64_t blob_bar;
     const int lane = threadIdx.x & 31;
@@ -799,17 +795,14 @@ bcp_kernel(DbDev db, BatchDev b, int warp_bytes, int qcap) {
     WarpCtx c;
     c.S = (uint64_t*)base;
     const int n_planes = db.n_lit + 4;
-    c.queue = (uint16_t*)(c.S + n_planes);
-    c.inq = (uint32_t*)(c.queue + qcap);  // qcap ring slots (one per literal, multiple of 4)
     const int inq_words = (db.n_lit + 31) >> 5;
-    c.tset = c.inq + ((inq_words + 1) & ~1);
-    c.dead = (uint64_t*)(c.tset + ((inq_words + 1) & ~1));
-    c.qtail = (uint32_t*)(c.dead + 1);
-    c.ntouched = c.qtail + 1;
-    c.qcap = (uint32_t)qcap;
-    c.qmagic = (uint32_t)((0x100000000ull + (uint32_t)qcap - 1) / (uint32_t)qcap);
+    const int iw2 = (inq_words + 1) & ~1;
+    c.fill = (uint32_t*)(c.S + n_planes);
+    c.drain = c.fill + iw2;
+    c.tset = c.drain + iw2;
+    c.dead = (uint64_t*)(c.tset + iw2);
     // 16-byte aligned: mbarriers, then the tiles the bulk copies write
-    uint64_t* ring_bar = (uint64_t*)(base + ((((unsigned char*)(c.qtail + 2) - base) + 15) & ~(size_t)15));
+    uint64_t* ring_bar = (uint64_t*)(base + ((((unsigned char*)(c.dead + 1) - base) + 15) & ~(size_t)15));
     const int stages = b.ring_stages;
     unsigned char* ring = (unsigned char*)(ring_bar + ((stages + 1) & ~1));
 
@@ -817,10 +810,7 @@ bcp_kernel(DbDev db, BatchDev b, int warp_bytes, int qcap) {
     // false" literal (FALSE plane all ones, TRUE plane 0), n_lit + 2 / + 3 = the pad variable of
     // gate records (TRUE plane 0, FALSE plane all ones: known, value 0)
     for (int i = lane; i < n_planes; i += 32) c.S[i] = (i == db.n_lit || i == db.n_lit + 3) ? ~0ull : 0ull;
-    for (int i = lane; i < inq_words; i += 32) {
-        c.inq[i] = 0;
-        c.tset[i] = 0;
-    }
+    for (int i = lane; i < 3 * iw2; i += 32) c.fill[i] = 0;
     if (lane == 0) {
         for (int s = 0; s < stages; s++) mbar_init(&ring_bar[s], 1);
         mbar_fence_init();
@@ -834,7 +824,7 @@ bcp_kernel(DbDev db, BatchDev b, int warp_bytes, int qcap) {
     const uint64_t stride = (uint64_t)gridDim.x * wpc;
     const uint64_t g_first = (uint64_t)blockIdx.x * wpc + warp;
 
-    // ---- producer side of the words ring (lane 0): group g_pf goes to stage pf_stage
+    // ---- producer side of the words ring (lane 0): group pf_g goes to stage pf_stage
     uint64_t pf_g = g_first;
     int pf_stage = 0;
     int pf_p = -1;
@@ -898,11 +888,7 @@ bcp_kernel(DbDev db, BatchDev b, int warp_bytes, int qcap) {
         // BCP can only start from a candidate record or a contradicted level-0 value
         const bool active = !db.unsat && (P_cand_cnt != 0 || (P_flags & POINT_HAS_FIXED) != 0 || b.assign != nullptr);
 
-        if (lane == 0) {
-            *c.dead = db.unsat ? valid : 0;
-            *c.qtail = 0;
-            *c.ntouched = 0;
-        }
+        if (lane == 0) *c.dead = db.unsat ? valid : 0;
         mbar_wait(&ring_bar[stage], phase);  // the group's words have landed
         __syncwarp();
 
@@ -930,7 +916,7 @@ bcp_kernel(DbDev db, BatchDev b, int warp_bytes, int qcap) {
         stage = stage + 1 == stages ? 0 : stage + 1;
         phase ^= (stage == 0);
 
-        uint32_t qh = 0;
+        uint32_t npops = 0;
         if (active) {
             // ---- (2) first wave over the point's candidate records
             if (P_cand_cnt) {
@@ -942,101 +928,123 @@ bcp_kernel(DbDev db, BatchDev b, int warp_bytes, int qcap) {
                     if (i + 32 < P_cand_cnt) r = __ldg(&list[i + 32]);
                     eval_record(cur, db.rec, c, live);
                 }
-                __syncwarp();
             }
 
-            // ---- (3) propagate the implied literals to the fixpoint.  Up to 32 queued literals
-            // are taken per round (one per lane); the gate lists of their variables, then the
-            // clause lists of their complements, are visited as one flattened list each, one
-            // record per lane per trip.
-            while (true) {
-                const uint32_t qt = *(volatile uint32_t*)c.qtail;
-                const uint64_t deadv = *(volatile uint64_t*)c.dead;
-                if (qh == qt || (deadv & valid) == valid) break;
-                const uint32_t np = min(qt - qh, (uint32_t)MULTI_POP);
-                uint32_t myl = 0, gbeg = 0, glen = 0, cbeg = 0, clen = 0;
-                if (lane < (int)np) myl = c.queue[ring_index(c, qh + lane)];
-                qh += np;
+            // ---- (3) level-synchronous propagation to the fixpoint.  The frontier of a level is
+            // a bitset; every lane owns the words lane, lane + 32, ... of it and hands out one
+            // literal per round.  The gate lists of the round's variables, then the clause lists
+            // of the literals' complements, are visited as one flattened list each, one record
+            // per lane per trip.
+            bool stop = false;
+            while (!stop) {
                 __syncwarp();
-                if (lane < (int)np) {
-                    atomicAnd(&c.inq[myl >> 5], ~(1u << (myl & 31)));
+                {
+                    uint32_t* t_ = c.fill;
+                    c.fill = c.drain;
+                    c.drain = t_;
+                }
+                uint32_t my_w = lane, my_bits = 0;
+                auto fetch = [&]() {
+                    while (my_bits == 0 && my_w < (uint32_t)inq_words) {
+                        const uint32_t v = c.drain[my_w];
+                        if (v) {
+                            c.drain[my_w] = 0;
+                            c.tset[my_w] |= v;
+                            my_bits = v;
+                        } else
+                            my_w += 32;
+                    }
+                };
+                fetch();
+                if (!__any_sync(0xffffffffu, my_bits != 0)) break;
+                do {
+                    const uint64_t deadv = *(volatile uint64_t*)c.dead;
+                    if ((deadv & valid) == valid) {
+                        stop = true;
+                        break;
+                    }
+                    const uint64_t live = valid & ~deadv;
+                    const bool have = my_bits != 0;
+                    uint32_t myl = 0;
+                    if (have) {
+                        const int bp = __ffs(my_bits) - 1;
+                        my_bits &= my_bits - 1;
+                        myl = 32u * my_w + bp;
+                    }
+                    fetch();
+                    npops += __popc(__ballot_sync(0xffffffffu, have));
                     if (db.n_gates) {
-                        const uint32_t v = myl >> 1;
-                        gbeg = gocc_off[v];
-                        glen = gocc_off[v + 1] - gbeg;
+                        uint32_t gbeg = 0, glen = 0;
+                        if (have) {
+                            const uint32_t v = myl >> 1;
+                            gbeg = gocc_off[v];
+                            glen = gocc_off[v + 1] - gbeg;
+                        }
+                        const uint32_t cum = warp_incl_scan(glen, lane);
+                        const uint32_t total = __shfl_sync(0xffffffffu, cum, 31);
+                        const uint32_t gbase = gbeg - (cum - glen);  // list index = gbase + i
+                        for (uint32_t i0 = 0; i0 < total; i0 += 32) {
+                            const uint32_t i = i0 + lane;
+                            const int q = find_owner(cum, i);
+                            const uint32_t bq = __shfl_sync(0xffffffffu, gbase, q & 31);
+                            if (i < total) {
+                                const uint4 r = grec[gocc[bq + i]];
+                                eval_gate(r, c, live);
+                            }
+                        }
                     }
                     if (db.n_rec) {
-                        const uint32_t nl = myl ^ 1;  // this literal just became false somewhere
-                        cbeg = occ_off[nl];
-                        clen = occ_off[nl + 1] - cbeg;
-                    }
-                }
-                const uint64_t live = valid & ~deadv;
-                if (db.n_gates) {
-                    const uint32_t cum = warp_incl_scan(glen, lane);
-                    const uint32_t total = __shfl_sync(0xffffffffu, cum, 31);
-                    const uint32_t gbase = gbeg - (cum - glen);  // list index = gbase + i
-                    for (uint32_t i0 = 0; i0 < total; i0 += 32) {
-                        const uint32_t i = i0 + lane;
-                        const int q = find_owner(cum, i);
-                        const uint32_t bq = __shfl_sync(0xffffffffu, gbase, q & 31);
-                        if (i < total) {
-                            const uint4 r = grec[gocc[bq + i]];
-                            eval_gate(r, c, live);
+                        uint32_t cbeg = 0, clen = 0;
+                        if (have) {
+                            const uint32_t nl = myl ^ 1;  // this literal just became false somewhere
+                            cbeg = occ_off[nl];
+                            clen = occ_off[nl + 1] - cbeg;
+                        }
+                        const uint32_t cum = warp_incl_scan(clen, lane);
+                        const uint32_t total = __shfl_sync(0xffffffffu, cum, 31);
+                        const uint32_t cbase = cbeg - (cum - clen);
+                        for (uint32_t i0 = 0; i0 < total; i0 += 32) {
+                            const uint32_t i = i0 + lane;
+                            const int q = find_owner(cum, i);
+                            const uint32_t bq = __shfl_sync(0xffffffffu, cbase, q & 31);
+                            if (i < total) {
+                                const uint4 r = __ldg(&db.occrec[bq + i]);
+                                eval_clause(r, db.rec, c, live);
+                            }
                         }
                     }
-                }
-                if (db.n_rec) {
-                    const uint32_t cum = warp_incl_scan(clen, lane);
-                    const uint32_t total = __shfl_sync(0xffffffffu, cum, 31);
-                    const uint32_t cbase = cbeg - (cum - clen);
-                    for (uint32_t i0 = 0; i0 < total; i0 += 32) {
-                        const uint32_t i = i0 + lane;
-                        const int q = find_owner(cum, i);
-                        const uint32_t bq = __shfl_sync(0xffffffffu, cbase, q & 31);
-                        if (i < total) {
-                            const uint4 r = __ldg(&db.occrec[bq + i]);
-                            eval_clause(r, db.rec, c, live);
-                        }
-                    }
-                }
-                __syncwarp();
+                    __syncwarp();
+                } while (__any_sync(0xffffffffu, my_bits != 0));
             }
-            acc.pops += qh;
+            acc.pops += npops;
             __syncwarp();
         }
 
         // ---- (4) per-sample results
         const uint64_t dead = *c.dead & valid;
         const uint64_t okm = valid & ~dead;
-        const uint32_t n_touched = *c.ntouched;
+        uint32_t n_touched = 0;
+        if (active) {
+            // everything implied in this group: visited literals + what an early stop left behind
+            uint32_t lcnt = 0;
+            for (int wi = lane; wi < inq_words; wi += 32) {
+                const uint32_t u = c.tset[wi] | c.fill[wi] | c.drain[wi];
+                c.tset[wi] = u;
+                lcnt += __popc(u);
+            }
+            n_touched = __reduce_add_sync(0xffffffffu, lcnt);
+        }
         acc.touched += n_touched;
         uint32_t cnt0, cnt1;  // assigned live variables of samples lane, lane+32
-        if (n_touched == 0) {
+        if (n_touched == 0 || okm == 0) {  // counts only matter for conflict-free samples
             cnt0 = cnt1 = P_n_assumed;
         } else {
-            // compact the implied literals (bits of tset) into the now idle queue array
-            uint32_t basew = 0;
-            for (int w0 = 0; w0 < inq_words; w0 += 32) {
-                const int wi = w0 + lane;
-                uint32_t bits = wi < inq_words ? c.tset[wi] : 0u;
-                const uint32_t pc = __popc(bits);
-                const uint32_t incl = warp_incl_scan(pc, lane);
-                uint32_t o = basew + incl - pc;
-                while (bits) {
-                    const int bpos = __ffs(bits) - 1;
-                    bits &= bits - 1;
-                    c.queue[o++] = (uint16_t)(32 * wi + bpos);
-                }
-                basew += __shfl_sync(0xffffffffu, incl, 31);
-            }
-            __syncwarp();
             // bit-sliced population count over the implied planes: per sample, how many
-            // literals of the undo list are set (each implied variable has one polarity per
+            // literals of the undo set are true (each implied variable has one polarity per
             // conflict-free sample)
-            if (n_touched < 256) count_planes<8>(c.S, c.queue, n_touched, lane, cnt0, cnt1);
-            else if (n_touched < 2048) count_planes<11>(c.S, c.queue, n_touched, lane, cnt0, cnt1);
-            else count_planes<MAX_COUNT_BITS>(c.S, c.queue, n_touched, lane, cnt0, cnt1);
+            if (n_touched < 256) count_planes<8>(c.S, c.tset, inq_words, lane, cnt0, cnt1);
+            else if (n_touched < 2048) count_planes<11>(c.S, c.tset, inq_words, lane, cnt0, cnt1);
+            else count_planes<MAX_COUNT_BITS>(c.S, c.tset, inq_words, lane, cnt0, cnt1);
             cnt0 += P_n_assumed;
             cnt1 += P_n_assumed;
         }
@@ -1045,7 +1053,7 @@ bcp_kernel(DbDev db, BatchDev b, int warp_bytes, int qcap) {
         const uint32_t full_hi = __ballot_sync(0xffffffffu, ok1 && cnt1 == (uint32_t)db.n_live);
         const uint64_t fullm = ((uint64_t)full_hi << 32) | full_lo;
         const uint32_t t0 = db.n_base_assigned + cnt0, t1 = db.n_base_assigned + cnt1;
-        if (n_touched == 0) {
+        if (n_touched == 0 || okm == 0) {
             const uint64_t nok = __popcll(okm);
             acc.sum += nok * t0;
             acc.sumsq += nok * (uint64_t)t0 * t0;
@@ -1100,7 +1108,7 @@ bcp_kernel(DbDev db, BatchDev b, int warp_bytes, int qcap) {
         }
         __syncwarp();
 
-        // ---- (5) undo: clear the assumption planes, the implied planes and the queue flags
+        // ---- (5) undo: clear the assumption planes, the implied planes and the frontier bitsets
         if (active) {
             for (uint32_t j = lane; j < k; j += 32) {
                 const uint32_t cd = j < 32 ? P_code0 : code[j];
@@ -1111,10 +1119,16 @@ bcp_kernel(DbDev db, BatchDev b, int warp_bytes, int qcap) {
                 }
             }
             if (n_touched) {
-                for (uint32_t i = lane; i < n_touched; i += 32) c.S[c.queue[i]] = 0;
-                for (int i = lane; i < inq_words; i += 32) {
-                    c.inq[i] = 0;
-                    c.tset[i] = 0;
+                for (int wi = lane; wi < inq_words; wi += 32) {
+                    uint32_t bits = c.tset[wi];
+                    while (bits) {
+                        const int bp = __ffs(bits) - 1;
+                        bits &= bits - 1;
+                        c.S[32 * wi + bp] = 0;
+                    }
+                    c.tset[wi] = 0;
+                    c.fill[wi] = 0;
+                    c.drain[wi] = 0;
                 }
             }
         }

@@ -194,11 +194,11 @@ static int sync_device_db(pdsat_db* db) {
     if (count_bits_for(h.n_live) > MAX_COUNT_BITS) return fail(PDSAT_ERR_LIMIT, "too many live variables for the counters");
     int n_lit = 2 * h.n_live;
     int n_planes = n_lit + 4;
-    int qcap = (n_lit + 2 + 3) & ~3;  // queue ring: one slot per literal
     int inq_words = (n_lit + 31) / 32;
-    int warp_bytes = n_planes * 8 + qcap * 2 + 2 * ((inq_words + 1) & ~1) * 4 + 16;
+    // planes + three bitsets (two frontiers, undo set) + the conflict mask
+    int warp_bytes = n_planes * 8 + 3 * ((inq_words + 1) & ~1) * 4 + 8;
     warp_bytes = (warp_bytes + 15) & ~15;
-    db->qcap = qcap;
+    db->qcap = 0;
     db->warp_bytes = warp_bytes;
     if (db->device < 0) {
         db->warps_per_cta = 0;
@@ -898,7 +898,7 @@ int pdsat_batch_propagate(pdsat_batch* b) {
         bd.peer.parity = parity;
         bd.peer.n_words = n_cost_words;
     }
-    bcp_kernel<<<grid, L.wpc * 32, L.smem_bytes, st>>>(dev, bd, L.warp_bytes, db->qcap);
+    bcp_kernel<<<grid, L.wpc * 32, L.smem_bytes, st>>>(dev, bd, L.warp_bytes);
     b->n_kernels++;
     if (b->peer_ranks > 0) {
         const unsigned long long target = (unsigned long long)(b->peer_step / 2 + 1) * b->peer_ranks;
