@@ -467,8 +467,16 @@ __device__ __forceinline__ uint64_t or64_shared(uint64_t* p, uint64_t v) {
 // make literal l true in the samples `bits` (Solver.cc:579-585 uncheckedEnqueue, for up to 64
 // samples at once).  Planes only gain bits; a literal that gained a bit joins the next frontier,
 // so every clause / gate that can react to it is visited (again).
+// A sample in which the complement is (or becomes) true as well is a CONFLICT: two reasons
+// implied opposite values, the later reason's clause is falsified (Solver.cc:641-646).  The check
+// is made here, after the own write: of two racing writers the later one sees the earlier one's
+// plane (shared-memory operations of a warp complete in order), so no such sample is missed.
+// Clauses would notice the contradiction by themselves (all their literals are false); two gates
+// that read the variable through opposite polarities would each see a value that suits them.
 __device__ __forceinline__ void set_true(const WarpCtx& c, uint32_t l, uint64_t bits) {
     const uint64_t old = or64_shared(&c.S[l], bits);
+    const uint64_t contra = bits & *(const volatile uint64_t*)&c.S[l ^ 1u];
+    if (contra) or64_shared(c.dead, contra);
     if (bits & ~old) atomicOr(&c.fill[l >> 5], 1u << (l & 31));
 }
 
@@ -481,6 +489,9 @@ __device__ __forceinline__ void set_pair(const WarpCtx& c, uint32_t tcode, uint6
     if (th) nt |= th & ~atomicOr(q + 1, th);
     if (fl) nf |= fl & ~atomicOr(q + 2, fl);
     if (fh) nf |= fh & ~atomicOr(q + 3, fh);
+    const volatile uint64_t* now = c.S + tcode;
+    const uint64_t contra = (t & now[1]) | (f & now[0]);
+    if (contra) or64_shared(c.dead, contra);
     const uint32_t m = (nt ? 1u : 0u) | (nf ? 2u : 0u);
     if (m) atomicOr(&c.fill[tcode >> 5], m << (tcode & 31));  // both literals sit in one word
 }
@@ -583,13 +594,12 @@ __device__ __forceinline__ void eval_gate(const uint4& r, const WarpCtx& c, uint
     const uint32_t tag = r.w >> 16;
     const uint64_t am = (tag & 2u) ? ~0ull : 0ull;  // ANDXOR
     uint64_t par = (tag & 1u) ? ~0ull : 0ull;       // p ^ xor(values): must end up 0
-    uint64_t any = 0, two = 0, both = 0;
+    uint64_t any = 0, two = 0;
     uint64_t u0, u1, u2, u3, u4;
     uint64_t t, f;
 #define PDSAT_XVAR(U, CODE)              \
     ld_pair(c.S, (CODE), t, f);          \
     U = ~(t | f);                        \
-    both |= t & f;                       \
     par ^= t;                            \
     two |= any & U;                      \
     any |= U;
@@ -614,11 +624,7 @@ __device__ __forceinline__ void eval_gate(const uint4& r, const WarpCtx& c, uint
     any |= m5;
     two |= any & m6;
     any |= m6;
-    // a member that two reasons made true AND false: the later reason's clause is falsified.
-    // (Clauses notice this by themselves - all their literals are false; two gates that read the
-    // variable through opposite polarities would each see a consistent value.)
-    both |= (tb & fb) | (tc & fc);
-    const uint64_t confl = ((~any & par) | both) & live;
+    const uint64_t confl = ~any & par & live;
     const uint64_t one = any & ~two & live;
     if (confl) or64_shared(c.dead, confl);
     if (one) {

@@ -55,3 +55,15 @@ for ln, v in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
         if 0 < ln[1] <= len(src[f]):
             text = src[f][ln[1] - 1].strip()[:90]
     print("%-22s %7.2f%% %6.1f %5.1f%%         %s" % ("%s:%d" % ln, 100.0 * v[0] / tot[0], v[1] / max(1, v[0]), 100.0 * v[2] / max(1, tot[2]), text))
+
+# optional: share of instruction count per line range "name:lo-hi,..." (argv[4])
+if len(sys.argv) > 4:
+    for spec in sys.argv[4].split(","):
+        name, rng = spec.split(":")
+        lo, hi = (int(x) for x in rng.split("-"))
+        a = [0, 0, 0]
+        for ln, v in agg.items():
+            if ln and ln[0] == "kernels.cuh" and lo <= ln[1] <= hi:
+                for j in range(3):
+                    a[j] += v[j]
+        print("%-14s lines %4d-%4d  instr %6.2f%%  lanes %5.1f  samples %5.1f%%" % (name, lo, hi, 100.0 * a[0] / tot[0], a[1] / max(1, a[0]), 100.0 * a[2] / max(1, tot[2])))
