@@ -129,44 +129,84 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- CPU arm
+# Everything below that touches oracle/ is the CHECKER or the reported CPU baseline, never the
+# product path.  One process per host core, static split of the sample range; the per-sample
+# loop runs in C (orc_batch_mt), so the figures are the solver's, not Python's.
+_CPU = {}
+
+
+def _cpu_oracle(kind, with_units):
+    key = (kind, with_units)
+    if key not in _CPU:
+        from oracle import oracle as orc
+        nv, cl, offs, lits, stream = instance()
+        O = orc.Oracle(nv, offs, lits, kind)
+        if with_units:
+            O.add_units(list(stream))
+        _CPU[key] = (O, [int(x) for x in stream])
+    return _CPU[key]
+
+
 def _cpu_worker(args):
-    kind, mode, seed, n = args
-    from oracle import oracle as orc
-    nv, cl, offs, lits, stream = instance()
-    O = orc.Oracle(nv, offs, lits, kind)
-    A = orc.sample_assumptions(seed, SET_VARS, 0, n)
-    st = list(stream)
+    """(kind, mode, seed, set_vars, first_sample, n, want) -> (seconds, sums, conflict bits, trail)"""
+    kind, mode, seed, set_vars, first, n, want = args
+    O, stream = _cpu_oracle(kind, mode == 0)
     t0 = time.perf_counter()
-    conf = 0
-    if mode == "faithful":
-        for s in range(n):
-            r, _ = O.predict_sample(list(A[s]) + st, 0, want_assigns=False)
-            conf += r.conflict
-    else:
-        O.add_units(st)
-        for s in range(n):
-            r, _ = O.bcp(A[s], want_assigns=False)
-            conf += r.conflict
-    return time.perf_counter() - t0, conf
+    conflict, full, trail, sums = O.batch_mt(mode, seed, set_vars, n, first_sample=first,
+                                             extra=stream if mode == 1 else (), want_trail=want)
+    dt = time.perf_counter() - t0
+    if want:
+        return dt, sums, np.packbits(conflict, bitorder="little"), trail
+    return dt, sums, None, None
 
 
-def cpu_arm(n_per_core: int, mode: str = "faithful", cores: int | None = None):
-    """Reference CPU path on all host cores (one process per core, static split — the
-    reference's master/worker MPI only adds dispatch overhead)."""
-    import multiprocessing as mp
+_POOL = None
+
+
+def cpu_pool():
+    global _POOL
+    if _POOL is None:
+        import multiprocessing as mp
+        from oracle import oracle as orc
+        orc.build()
+        _POOL = mp.get_context("spawn").Pool(os.cpu_count() or 1)
+    return _POOL
+
+
+def cpu_kind():
     from oracle import oracle as orc
     orc.build()
-    kind = "ref" if orc.have_ref() else "port"
+    return "ref" if orc.have_ref() else "port"
+
+
+def cpu_run(mode, seed, set_vars, n, first_sample=0, want=False, cores=None):
+    """Reference CPU path over samples [first_sample, first_sample + n) on all host cores.
+    mode 1 = solverProgramCalling (fresh Solver + addProblem per sample, eval=prep),
+    mode 0 = BCP only on a persistent clause DB."""
     cores = cores or os.cpu_count() or 1
-    ctx = mp.get_context("spawn")
+    kind = cpu_kind()
+    cuts = [first_sample + n * i // cores for i in range(cores + 1)]
+    jobs = [(kind, mode, seed, list(set_vars), cuts[i], cuts[i + 1] - cuts[i], want) for i in range(cores)
+            if cuts[i + 1] > cuts[i]]
     t0 = time.perf_counter()
-    with ctx.Pool(cores) as pool:
-        res = pool.map(_cpu_worker, [(kind, mode, 1000 + i, n_per_core) for i in range(cores)])
+    res = cpu_pool().map(_cpu_worker, jobs)
     wall = time.perf_counter() - t0
     busy = max(r[0] for r in res)
-    return {"value": cores * n_per_core / busy, "unit": "samples/s", "cores": cores,
-            "kind": "reference" if kind == "ref" else "port", "wall_s": wall,
-            "sample": "%d samples/core x %d cores, %s" % (n_per_core, cores,
+    sums = [sum(r[1][j] for r in res) for j in range(6)]
+    out = {"n": n, "cores": len(jobs), "busy_s": busy, "wall_s": wall, "samples_per_s": n / busy, "sums": sums,
+           "kind": "reference" if kind == "ref" else "port"}
+    if want:
+        out["conflict"] = np.concatenate([np.unpackbits(r[2], bitorder="little")[:j[5]].astype(bool)
+                                          for r, j in zip(res, jobs)])
+        out["trail"] = np.concatenate([r[3] for r in res])
+    return out
+
+
+def cpu_arm(n_per_core, mode="faithful", cores=None):
+    cores = cores or os.cpu_count() or 1
+    r = cpu_run(1 if mode == "faithful" else 0, 1000, SET_VARS, n_per_core * cores, cores=cores)
+    return {"value": r["samples_per_s"], "unit": "samples/s", "cores": r["cores"], "kind": r["kind"],
+            "sample": "%d samples/core x %d cores, %s" % (n_per_core, r["cores"],
                       "fresh Solver + addProblem per sample (solverProgramCalling, eval=prep)" if mode == "faithful"
                       else "persistent clause DB, BCP only")}
 
@@ -176,15 +216,13 @@ def run_reference(args):
     if rank != 0:
         return
     n_per_core = args.cpu_samples
-    for _ in range(args.warmup):
-        cpu_arm(max(50, n_per_core // 10))
-    vals = []
-    t_all = 0.0
     cores = os.cpu_count() or 1
+    for _ in range(min(args.warmup, 1)):
+        cpu_arm(max(20, n_per_core // 10))
+    t_all = 0.0
     last = None
     for _ in range(args.steps):
         last = cpu_arm(n_per_core)
-        vals.append(last["value"])
         t_all += cores * n_per_core / last["value"]
     v = cores * n_per_core * args.steps / t_all
     line = {"impl": "reference", "metric": "decomp-set samples/sec", "value": v, "unit": "samples/s",
@@ -203,6 +241,62 @@ def workload_config(n_samples):
                         "30-var start-state set {148..177}, mt19937 bool_rand samples, predict (eval=prep/propagation)",
             "samples_per_gpu_per_step": n_samples, "set_size": len(SET_VARS),
             "l2": "flushed between timed steps (256 MiB write)"}
+
+
+# ----------------------------------------------------------------------------- parity + cascade legs
+def gpu_vs_cpu_per_sample(api, db, set_vars, seed, n, first_sample=0):
+    """EVERY sample of the batch: conflict flag and trail (= Solver::propagations of a
+    conflict-free sample) of the device against the reference BCP on the host cores."""
+    b = api.Batch(db, [api.Point(list(set_vars), n, api.MODE_MT19937, seed=seed, first_sample=first_sample)],
+                  api.OUT_FLAGS | api.OUT_TRAIL)
+    cost = b.run()[0]
+    conflict, _ = b.flags(0)
+    trail = b.trail(0)
+    b.close()
+    cpu = cpu_run(0, seed, set_vars, n, first_sample=first_sample, want=True)
+    ok = ~cpu["conflict"]
+    bad_c = int((conflict != cpu["conflict"]).sum())
+    bad_t = int((trail[ok] != cpu["trail"][ok]).sum())
+    sums_ok = (cost.n_conflict == cpu["sums"][0] and cost.sum_trail == cpu["sums"][2]
+               and cost.sumsq_trail == cpu["sums"][3])
+    return {"samples": n, "conflict_mismatches": bad_c, "trail_mismatches": bad_t, "integer_sums_equal": bool(sums_ok),
+            "checker": "oracle/_ref (unmodified reference MiniSat)" if cpu["kind"] == "reference" else "oracle port",
+            "cpu_bcp_only_samples_per_s": cpu["samples_per_s"], "cpu_cores": cpu["cores"],
+            "cpu_propagations": cpu["sums"][4], "cpu_watch_scans": cpu["sums"][5]}, cost
+
+
+def work_equivalent_bytes(nv, clauses, stream, set_vars, seed, n_probe=400):
+    """SURVEY.md 8(d) byte formula on a probe of samples (what a per-sample watched-literal BCP
+    touches): mean over conflict-free samples of sum_{p in T} [4|occ(~p)| + 4 sum|c|] + 4|T| + 8."""
+    from oracle import oracle as orc
+    O, st = _cpu_oracle(cpu_kind(), True)
+    occ_cost = {}
+    for c in clauses:
+        for l in c:
+            a = occ_cost.setdefault(l, [0, 0])
+            a[0] += 1
+            a[1] += len(c)
+    A = orc.sample_assumptions(seed, set_vars, 0, n_probe)
+    tot, cnt = 0, 0
+    for s in range(n_probe):
+        r, asg = O.bcp(list(A[s]))
+        if r.conflict:
+            continue
+        b = 8
+        for v in range(nv):
+            if asg[v] == 2:
+                continue
+            p = (v + 1) if asg[v] == 0 else -(v + 1)
+            oc = occ_cost.get(-p, (0, 0))
+            b += 4 * oc[0] + 4 * oc[1] + 4
+        tot += b
+        cnt += 1
+    return tot / cnt if cnt else None
+
+
+def load_profile_metrics():
+    tp = os.path.join(ROOT, "profiles", "bcp_kernel_metrics.json")
+    return json.load(open(tp)) if os.path.exists(tp) else {}
 
 
 # ----------------------------------------------------------------------------- GPU arm
@@ -246,23 +340,7 @@ def run_ours(args):
     # separate NCCL all-reduce for comparison
     reduce_mode = "none"
     if dist is not None:
-        reduce_mode = "nccl"
-        if args.reduce in ("peer", "auto"):
-            try:
-                mine = torch.frombuffer(bytearray(batch.peer_export()), dtype=torch.uint8).cuda()
-                allh = [torch.empty(64, dtype=torch.uint8, device="cuda") for _ in range(world)]
-                dist.all_gather(allh, mine)
-                batch.peer_connect([bytes(h.cpu().numpy().tobytes()) for h in allh], rank)
-                reduce_mode = "peer"
-            except Exception as e:  # IPC unavailable: fall back to NCCL, and say so
-                if rank == 0:
-                    print("peer reduce unavailable (%s); using NCCL all-reduce" % e, file=sys.stderr)
-        ok = torch.tensor([1 if reduce_mode == "peer" else 0], device="cuda")
-        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-        if reduce_mode == "peer" and int(ok.item()) == 0:
-            batch.peer_disconnect()
-            reduce_mode = "nccl"
-        dist.barrier()
+        reduce_mode = connect_peers(torch, dist, batch, rank, world, args.reduce)
     use_nccl = reduce_mode == "nccl"
 
     def barrier():
@@ -273,9 +351,9 @@ def run_ours(args):
     # ---------------- device-timed: inputs resident in HBM
     batch.fill()
     torch.cuda.synchronize()
-    launches0 = batch.launch_count()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     sampler = ClockSampler(local_rank)
+    kernel_ms_all = []
     for w in range(args.warmup):
         flush.zero_()
         batch.propagate()
@@ -339,83 +417,58 @@ def run_ours(args):
             break
     clocks = sampler.stop()
     clocks["note"] = "sampled across the timed regions plus 1.5 s of the same fill+propagate load"
+    if dist is not None:
+        dist.barrier()
+    batch.close()
 
-    # ---------------- secondary workloads (rank 0 only, not part of the headline): a cascade-
-    # heavy set (k = 86: ~40 % conflicts, ~60 % of the samples imply literals) and solve-mode
-    # enumeration of 2^24 assignments of the weakened-Bivium stand-in
+    prof = load_profile_metrics()
+    info = db.info()
     extra = {}
+    parity = None
+    cascade = {}
     if rank == 0 and not args.no_extra:
-        sv86 = [177 - i for i in range(86)]
-        n86 = 2_000_000
-        b86 = api.Batch(db, [api.Point(sv86, n86, api.MODE_MT19937, seed=1)])
-        for _ in range(3):
-            c86 = b86.run()[0]
-        f86, p86 = b86.last_ms()
-        extra["cascade_k86"] = {"samples": n86, "propagate_ms": p86, "fill_ms": f86,
-                                "samples_per_s": n86 / (p86 * 1e-3), "conflict_frac": c86.n_conflict / n86,
-                                "mean_trail_conflict_free": c86.sum_trail / max(1, n86 - c86.n_conflict),
-                                "propagated_literals_per_s": c86.sum_trail / (p86 * 1e-3)}
-        b86.close()
-        secret = mt19937_bool_rand_numpy(SECRET_SEED, 177)
-        db2 = api.ClauseDb(nv, offs, lits, device=local_rank)
-        db2.set_stream(stream_t.cuda_stream)
-        db2.set_fixed_assumptions(list(stream) + [2 * v + (0 if secret[v] else 1) for v in range(153)])
-        sv_enum = list(range(154, 178))
-        be = api.Batch(db2, [api.Point(sv_enum, 1 << 24, api.MODE_ENUM)], max_models=16)
-        for _ in range(3):
-            ce = be.run()[0]
-        fe, pe = be.last_ms()
-        found, _, smp, _ = be.models()
-        expect = sum(int(secret[153 + r]) << r for r in range(24))
-        extra["solve_enum_2^24"] = {"assignments": 1 << 24, "propagate_ms": pe, "fill_ms": fe,
-                                    "assignments_per_s": (1 << 24) / ((pe + fe) * 1e-3), "conflicts": ce.n_conflict,
-                                    "models": int(found), "secret_found": bool(found >= 1 and expect in [int(x) for x in smp])}
-        be.close()
-        db2.close()
-        # tabu-search step (config 3 shape): centre {148..177} + its 177 Hamming-1 neighbours in
-        # ONE batch, per-point mt19937 streams (seed = 1 + point), through the public call sequence
-        from pdsat_b200 import predicter as pr
-        sets = [SET_VARS] + pr.hamming1_neighbourhood(SET_VARS, list(range(1, 178)))
-        n_pt = 200_000
-        bn = api.Batch(db, [api.Point(sv, n_pt, api.MODE_MT19937, seed=1 + i) for i, sv in enumerate(sets)])
-        bn.run()
-        torch.cuda.synchronize()
-        t_n = time.perf_counter()
-        for _ in range(3):
-            cn = bn.run()
-        t_n = (time.perf_counter() - t_n) / 3
-        fn, pn = bn.last_ms()
-        extra["tabu_neighbourhood_178pts"] = {"points": len(sets), "samples_per_point": n_pt, "e2e_ms": t_n * 1e3,
-                                              "fill_ms": fn, "propagate_ms": pn,
-                                              "samples_per_s_e2e": len(sets) * n_pt / t_n,
-                                              "points_per_s": len(sets) / t_n}
-        bn.close()
-        # ODLS order-10 pair CNF (config 5: clause DB >> shared memory, 10-literal clauses):
-        # 8 cells of square A get a random value each (one-hot over the cell's 10 variables)
-        from pdsat_b200 import fixtures as fx
-        onv, ocl = fx.odls_pair_cnf(10)
-        ooffs, olits = fx.to_csr(ocl)
-        odb = api.ClauseDb(onv, ooffs, olits, device=local_rank)
-        odb.set_stream(stream_t.cuda_stream)
-        cells = [(1, 1), (1, 2), (2, 3), (3, 4), (4, 6), (5, 7), (6, 8), (8, 9)]
-        ovars = [fx.odls_var(10, 0, i, j, z) for (i, j) in cells for z in range(10)]
-        n_o = 100_000
-        rng = np.random.default_rng(3)
-        pick = rng.integers(0, 10, size=(n_o, len(cells)))
-        vals = np.zeros((n_o, len(ovars)), dtype=np.uint8)
-        for ci in range(len(cells)):
-            vals[np.arange(n_o), ci * 10 + pick[:, ci]] = 1
-        bo = api.Batch(odb, [api.Point(ovars, n_o, api.MODE_EXPLICIT, explicit_values=vals)])
-        for _ in range(3):
-            co = bo.run()[0]
-        fo, po = bo.last_ms()
-        oi = odb.info()
-        extra["odls10_predict"] = {"samples": n_o, "set_size": len(ovars), "propagate_ms": po, "fill_ms": fo,
-                                   "samples_per_s": n_o / (po * 1e-3), "conflict_frac": co.n_conflict / n_o,
-                                   "mean_trail_conflict_free": co.sum_trail / max(1, n_o - co.n_conflict),
-                                   "warps_per_cta": oi.warps_per_cta, "clauses": int(oi.n_clauses_live)}
-        bo.close()
-        odb.close()
+        # ---------------- per-sample parity of the WHOLE headline batch
+        parity, _ = gpu_vs_cpu_per_sample(api, db, SET_VARS, seed0, n, first_sample=first)
+        # ---------------- cascade sets: where BCP actually propagates.  k = 86: ~40 % conflicts,
+        # ~60 % of the samples imply literals; k >= 90: every sample conflicts (at different depths)
+        for k in args.cascade:
+            sv = [177 - i for i in range(k)]
+            nk = args.cascade_samples
+            bk = api.Batch(db, [api.Point(sv, nk, api.MODE_MT19937, seed=seed0)])
+            bk.fill()
+            for _ in range(3):
+                flush.zero_()
+                bk.propagate()
+            ms = []
+            for _ in range(5):
+                flush.zero_()
+                bk.propagate()
+                ms.append(bk.last_ms()[1])
+            ck = bk.costs()[0]
+            fk, _ = bk.last_ms()
+            bk.close()
+            par_k, _ = gpu_vs_cpu_per_sample(api, db, sv, seed0, nk)
+            med = statistics.median(ms)
+            n_ok = nk - ck.n_conflict
+            # literals BCP handled per sample: the k assumptions + what it implied (the level-0
+            # literals folded at upload are NOT counted); conflict samples: assumptions only
+            lits = (ck.sum_trail - n_ok * info.n_base_assigned) + ck.n_conflict * k
+            weq = work_equivalent_bytes(nv, cl, stream, sv, seed0) if n_ok else None
+            entry = {"samples": nk, "propagate_ms": med, "propagate_ms_all": ms, "fill_ms": fk,
+                     "samples_per_s": nk / (med * 1e-3), "conflict_frac": ck.n_conflict / nk,
+                     "implied_any_frac": ck.n_implied_any / nk,
+                     "mean_implied_per_ok_sample": ((ck.sum_trail / n_ok) - info.n_base_assigned - k) if n_ok else None,
+                     "propagated_literals_per_s": lits / (med * 1e-3),
+                     "literal_visits_per_group": ck.queue_pops / ((nk + 63) // 64),
+                     "parity": par_k,
+                     "speedup_vs_cpu_bcp_only": (nk / (med * 1e-3)) / par_k["cpu_bcp_only_samples_per_s"],
+                     "work_equivalent": None if weq is None else {
+                         "bytes_per_ok_sample": weq, "gbs": weq * n_ok / (med * 1e-3) / 1e9,
+                         "note": "SURVEY.md 8(d) formula (what a per-sample watched-literal BCP touches); "
+                                 "a work measure, not a bandwidth"},
+                     "ncu": prof.get("k%d" % k)}
+            cascade["k%d" % k] = entry
+        extra["cascade"] = cascade
 
     t = torch.tensor([dev_ms, e2e_s * 1e3, float(kernel_ms)], dtype=torch.float64, device="cuda")
     if dist is not None:
@@ -423,31 +476,34 @@ def run_ours(args):
     dev_ms, e2e_ms, kernel_ms = (float(x) for x in t.tolist())
 
     if rank == 0:
-        info = db.info()
         total = n * world * args.steps
         value = total / (dev_ms * 1e-3)
         e2e_value = total / (e2e_ms * 1e-3)
-        # roofline: T = 30 set literals + 200 keystream literals, nothing implied
-        true_lits = [int(l >> 1) + 1 if (l & 1) == 0 else -(int(l >> 1) + 1) for l in stream] + SET_VARS
-        bytes_per_sample = algorithmic_bytes_per_sample(nv, cl, true_lits)
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
         if os.path.exists(peaks_path):
             peak = json.load(open(peaks_path))["hbm_gbs"]
             peak_src = "measured (MEASURED_PEAKS.json)"
         else:
             peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-        achieved = bytes_per_sample * n / (kernel_ms * 1e-3) / 1e9
-        traffic = None
-        tp = os.path.join(ROOT, "profiles", "bcp_kernel_traffic.json")
-        if os.path.exists(tp):
-            per_sample = json.load(open(tp)).get("dram_bytes_per_sample")
-            traffic = per_sample * n if per_sample else None
+        # Roofline of the timed kernel on the bytes it must move: the bit-sliced assumption words
+        # (k rounded up to even, 8 bytes per 64 samples each) in, 64 bytes of accumulators out.
+        kp = (len(SET_VARS) + 1) & ~1
+        groups = (n + 63) // 64
+        alg_bytes = groups * kp * 8 + 64
+        achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
+        ph = prof.get("headline_k30", {})
+        traffic = ph.get("dram_bytes_per_sample")
+        traffic = traffic * n if traffic else None
+        true_lits = [int(l >> 1) + 1 if (l & 1) == 0 else -(int(l >> 1) + 1) for l in stream] + SET_VARS
+        weq = algorithmic_bytes_per_sample(nv, cl, true_lits)
         line = {
             "metric": "decomp-set samples/sec", "value": value, "unit": "samples/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
             "config": workload_config(n),
-            "propagated_literals_per_s": value * (info.n_base_assigned + len(SET_VARS)),
+            # per sample BCP handles the 30 assumed literals and implies nothing on this set; the 200
+            # keystream literals are folded once at upload and are not counted
+            "propagated_literals_per_s": value * len(SET_VARS),
             "e2e": {"value": e2e_value, "unit": "samples/s",
                     "h2d_bytes_per_step": int(h2d_per_step), "d2h_bytes_per_step": 8 * api.COST_WORDS,
                     "note": "inputs are descriptors (set, seed, window): sample values are generated on the "
@@ -455,37 +511,62 @@ def run_ours(args):
             "gpu_launches": int(gpu_launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                         "bytes_per_sample": bytes_per_sample,
-                         "dram_achieved_gbs": (traffic / (kernel_ms * 1e-3) / 1e9) if traffic else None,
-                         "note": "algorithmic bytes of SURVEY.md 8(d) = what a per-sample watched-literal BCP "
-                                 "touches (T=230 literals); this kernel folds the 200 keystream units at upload, "
-                                 "proves statically (first-wave candidate analysis) which clauses can fire and "
-                                 "shares index reads across 64 samples, so frac >> 1; the physical HBM traffic is "
-                                 "`traffic` (assumption words only) - see DESIGN.md"},
+                         "bytes_per_launch": alg_bytes, "bytes_per_sample": alg_bytes / n,
+                         "kernel": "bcp_kernel", "kernel_ms": kernel_ms,
+                         "ncu": ph or None,
+                         "work_equivalent": {"bytes_per_sample": weq, "gbs": weq * n / (kernel_ms * 1e-3) / 1e9,
+                                             "note": "SURVEY.md 8(d) formula for T = 230 true literals: what a "
+                                                     "per-sample watched-literal BCP touches - a work measure"},
+                         "note": "achieved = bytes the kernel must read (bit-sliced assumption words) / CUDA-event "
+                                 "time of the launch.  On this set the first-wave candidate list is empty: the kernel "
+                                 "streams the words and accounts 64 samples per group; the sets on which BCP "
+                                 "propagates are in extra.cascade (DESIGN.md section 5)"},
             "clocks": clocks,
             "kernel_ms_last": kernel_ms, "fill_ms_last": fill_ms_last, "wall_ms_per_step": 1e3 * t_wall / args.steps,
             "check": {"n": int(n_total_check), "n_conflict": int(costs_host.n_conflict),
                       "sum_trail": int(costs_host.sum_trail), "n_after_reduce": int(n_reduced_check)},
+            "parity": parity,
             "reduce": reduce_mode,
             "extra": extra,
             "launch": {"grid": info.grid, "warps_per_cta": info.warps_per_cta, "smem_bytes": info.smem_bytes,
-                       "live_vars": info.n_live_vars, "live_clauses": info.n_clauses_live},
+                       "live_vars": info.n_live_vars, "live_clauses": info.n_clauses_live, "gates": info.n_gates,
+                       "index_blob_bytes": info.blob_bytes, "index_blob_in_smem": bool(info.db_in_smem)},
         }
         if world == 1 and not args.no_cpu:
             cb = cpu_arm(args.cpu_samples, "faithful")
-            cb2 = cpu_arm(args.cpu_samples * 40, "bcp")
+            cb2 = cpu_arm(args.cpu_samples * 400, "bcp")
             cb["bcp_only_value"] = cb2["value"]
             cb["bcp_only_sample"] = cb2["sample"]
-            cb.pop("wall_s", None)
             line["cpu_baseline"] = cb
         print(json.dumps(line))
     if dist is not None:
         dist.barrier()  # nobody frees a peer-mapped buffer while another rank may still use it
-    batch.close()
     db.close()
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def connect_peers(torch, dist, batch, rank, world, want):
+    """Exchange the CUDA IPC handles of the ranks' reduce buffers; returns "peer" or "nccl"."""
+    mode = "nccl"
+    if want in ("peer", "auto"):
+        try:
+            mine = torch.frombuffer(bytearray(batch.peer_export()), dtype=torch.uint8).cuda()
+            allh = [torch.empty(64, dtype=torch.uint8, device="cuda") for _ in range(world)]
+            dist.all_gather(allh, mine)
+            batch.peer_connect([bytes(h.cpu().numpy().tobytes()) for h in allh], rank)
+            mode = "peer"
+        except Exception as e:  # IPC unavailable: fall back to NCCL, and say so
+            if rank == 0:
+                print("peer reduce unavailable (%s); using NCCL all-reduce" % e, file=sys.stderr)
+    ok = torch.tensor([1 if mode == "peer" else 0], device="cuda")
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    if mode == "peer" and int(ok.item()) == 0:
+        batch.peer_disconnect()
+        mode = "nccl"
+    dist.barrier()
+    return mode
 
 
 def main():
@@ -495,9 +576,12 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--samples", type=int, default=10_000_000, help="samples per GPU per step")
-    ap.add_argument("--cpu-samples", type=int, default=1500, help="CPU-arm samples per core per step")
+    ap.add_argument("--cpu-samples", type=int, default=1000, help="CPU-arm samples per core per step")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--no-extra", action="store_true", help="skip the secondary workloads")
+    ap.add_argument("--no-extra", action="store_true", help="skip the parity / cascade / multi-GPU workload legs")
+    ap.add_argument("--cascade", type=lambda v: [int(x) for x in v.split(",") if x], default=[86, 90, 100, 120, 177],
+                    help="set sizes (bivium_Ending2 prefixes) of the timed + parity-checked cascade legs")
+    ap.add_argument("--cascade-samples", type=int, default=1_000_000)
     ap.add_argument("--reduce", default="auto", choices=["auto", "peer", "nccl"],
                     help="N > 1: fused NVLink peer-memory reduce (auto/peer; falls back to NCCL if CUDA IPC "
                          "is unavailable) or the separate NCCL all-reduce (DESIGN.md section 6)")

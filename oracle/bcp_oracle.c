@@ -433,6 +433,47 @@ void orc_sample_assumptions(uint32_t seed, const int32_t* set_vars /*1-based*/, 
         }
 }
 
+/* Batch form of the predict path for the bench / full-size parity checks (loops in C instead of
+ * one ctypes call per sample).  Samples first_sample .. first_sample+n-1 of the 1-worker order
+ * (mpi_predicter.cpp:3236-3242) starting `first_draw` draws into mt19937(seed).
+ *   mode 0: BCP only on the persistent DB (orc_bcp)
+ *   mode 1: fresh solver + addProblem per sample, eval "prep" (orc_predict_sample)
+ * Per sample: bit s of conflict_bits / full_bits, trail[s] (0 for conflict samples);
+ * sums[0..5] += n_conflict, n_full, sum trail, sum trail^2, propagations, watch_scans
+ * (trail sums over conflict-free samples).  Any output pointer may be NULL. */
+void orc_batch_mt(void* hv, int mode, uint32_t seed, const int32_t* set_vars, int k, const int32_t* extra, int n_extra,
+                  uint64_t first_draw, uint64_t first_sample, uint64_t n, uint64_t* conflict_bits, uint64_t* full_bits,
+                  uint32_t* trail, uint64_t* sums) {
+    mt19937_t g;
+    mt_seed(&g, seed);
+    for (uint64_t i = 0; i < first_draw + first_sample * (uint64_t)k; i++) (void)mt_next(&g);
+    int32_t* a = (int32_t*)malloc(sizeof(int32_t) * (size_t)(k + n_extra + 1));
+    for (uint64_t s = 0; s < n; s++) {
+        for (int j = 0; j < k; j++) {
+            int b = (mt_next(&g) >> 31) == 0;
+            a[j] = 2 * (set_vars[j] - 1) + (b ? 0 : 1);
+        }
+        for (int j = 0; j < n_extra; j++) a[k + j] = extra[j];
+        orc_result r;
+        if (mode == 0) orc_bcp(hv, a, k, &r, NULL);
+        else orc_predict_sample(hv, a, k + n_extra, 0, &r, NULL);
+        if (conflict_bits && r.conflict) conflict_bits[s >> 6] |= 1ull << (s & 63);
+        if (full_bits && r.full) full_bits[s >> 6] |= 1ull << (s & 63);
+        if (trail) trail[s] = r.conflict ? 0u : (uint32_t)r.trail_size;
+        if (sums) {
+            sums[0] += (uint64_t)r.conflict;
+            sums[1] += (uint64_t)r.full;
+            if (!r.conflict) {
+                sums[2] += (uint64_t)r.trail_size;
+                sums[3] += (uint64_t)r.trail_size * (uint64_t)r.trail_size;
+            }
+            sums[4] += r.propagations;
+            sums[5] += r.watch_scans;
+        }
+    }
+    free(a);
+}
+
 /* ---------------------------------------------------------------- enumeration order
  * src_mpi/mpi_base.cpp:107-178 MakeAssignsFromMasks: bit r of lint <-> r-th variable
  * (ascending var index) of the variate part; set bit => positive literal. */

@@ -56,6 +56,9 @@ def _lib(kind: str):
     L.orc_add_units.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
     L.orc_predict_sample.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(OrcResult), C.c_void_p]
     L.orc_bcp.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(OrcResult), C.c_void_p]
+    L.orc_batch_mt.restype = None
+    L.orc_batch_mt.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_uint64,
+                               C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     if kind == "port":
         L.orc_mt19937_draws.argtypes = [C.c_uint32, C.c_uint64, C.c_uint64, C.c_void_p]
         L.orc_bool_rand.argtypes = [C.c_uint32, C.c_uint64, C.c_uint64, C.c_void_p]
@@ -118,6 +121,26 @@ class Oracle:
         asg = np.empty(self.n_vars, dtype=np.uint8) if want_assigns else None
         self.L.orc_bcp(self.h, a.ctypes.data, len(a), C.byref(r), asg.ctypes.data if want_assigns else None)
         return r, asg
+
+    def batch_mt(self, mode: int, seed: int, set_vars: Sequence[int], n: int, first_sample: int = 0,
+                 first_draw: int = 0, extra: Sequence[int] = (), want_trail: bool = True):
+        """Samples of the 1-worker mt19937 order, looped in C.  mode 0 = BCP only on the persistent
+        DB, 1 = fresh solver per sample (solverProgramCalling, eval prep; `extra` literals assumed
+        in every sample).  Returns (conflict[n] bool, full[n] bool, trail[n] uint32 | None,
+        sums = [n_conflict, n_full, sum_trail, sumsq_trail, propagations, watch_scans])."""
+        sv = np.ascontiguousarray(set_vars, dtype=np.int32)
+        ex = np.ascontiguousarray(extra, dtype=np.int32)
+        g = (n + 63) // 64
+        cb = np.zeros(g, dtype=np.uint64)
+        fb = np.zeros(g, dtype=np.uint64)
+        tr = np.zeros(n, dtype=np.uint32) if want_trail else None
+        sums = np.zeros(6, dtype=np.uint64)
+        self.L.orc_batch_mt(self.h, mode, seed, sv.ctypes.data, len(sv), ex.ctypes.data if len(ex) else None, len(ex),
+                            first_draw, first_sample, n, cb.ctypes.data, fb.ctypes.data,
+                            tr.ctypes.data if want_trail else None, sums.ctypes.data)
+        conflict = np.unpackbits(cb.view(np.uint8), bitorder="little")[:n].astype(bool)
+        full = np.unpackbits(fb.view(np.uint8), bitorder="little")[:n].astype(bool)
+        return conflict, full, tr, [int(x) for x in sums]
 
     # ---- reference-only entry points
     def solve_assumps(self, assumps: Sequence[int], max_nof_restarts: int = 0):

@@ -18,6 +18,7 @@
 // reference legs may load this library.  Nothing under pdsat_b200/ does.
 #include <cstdint>
 #include <cstring>
+#include <random>
 #include <string>
 #include <vector>
 
@@ -203,6 +204,42 @@ int orc_bcp(void* hv, const int32_t* assumps, int n, orc_result* r, uint8_t* ass
     fill_assigns(*S, h->n_vars, assigns);
     S->undo();
     return 0;
+}
+
+// Batch form of the predict path (bench / full-size parity): samples in the 1-worker order
+// (mpi_predicter.cpp:3236-3242) of std::mt19937(seed) - the same engine as boost::mt19937 -
+// with bool_rand == ((draw >> 31) == 0) (addit_func.cpp:193-196, Boost's bucket rule).
+//   mode 0: BCP only on the persistent DB;  mode 1: solverProgramCalling, eval "prep"
+// (fresh Solver + addProblem per sample; `extra` = literals assumed in every sample).
+void orc_batch_mt(void* hv, int mode, uint32_t seed, const int32_t* set_vars, int k, const int32_t* extra, int n_extra,
+                  uint64_t first_draw, uint64_t first_sample, uint64_t n, uint64_t* conflict_bits, uint64_t* full_bits,
+                  uint32_t* trail, uint64_t* sums) {
+    std::mt19937 gen(seed);
+    gen.discard(first_draw + first_sample * (uint64_t)k);
+    std::vector<int32_t> a((size_t)(k + n_extra));
+    for (uint64_t s = 0; s < n; s++) {
+        for (int j = 0; j < k; j++) {
+            bool b = (gen() >> 31) == 0;
+            a[j] = 2 * (set_vars[j] - 1) + (b ? 0 : 1);
+        }
+        for (int j = 0; j < n_extra; j++) a[k + j] = extra[j];
+        orc_result r;
+        if (mode == 0) orc_bcp(hv, a.data(), k, &r, nullptr);
+        else orc_predict_sample(hv, a.data(), k + n_extra, 0, &r, nullptr);
+        if (conflict_bits && r.conflict) conflict_bits[s >> 6] |= 1ull << (s & 63);
+        if (full_bits && r.full) full_bits[s >> 6] |= 1ull << (s & 63);
+        if (trail) trail[s] = r.conflict ? 0u : (uint32_t)r.trail_size;
+        if (sums) {
+            sums[0] += (uint64_t)r.conflict;
+            sums[1] += (uint64_t)r.full;
+            if (!r.conflict) {
+                sums[2] += (uint64_t)r.trail_size;
+                sums[3] += (uint64_t)r.trail_size * (uint64_t)r.trail_size;
+            }
+            sums[4] += r.propagations;
+            sums[5] += r.watch_scans;
+        }
+    }
 }
 
 // mpi_solver.cpp:218-245: incremental solve under assumptions + classification
