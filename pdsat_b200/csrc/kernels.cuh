@@ -434,6 +434,25 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) {
     }
 }
+// the same on 32-bit shared-window addresses (hot loops: no generic -> shared conversion)
+__device__ __forceinline__ void mbar_expect_tx_s(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait_s(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
 
 // ------------------------------------------------------------------ BCP
 // Per-warp working set in shared memory (one warp owns one group of 64 samples):
@@ -830,29 +849,32 @@ bcp_kernel(DbDev db, BatchDev b, int warp_bytes) {
     const uint64_t stride = (uint64_t)gridDim.x * wpc;
     const uint64_t g_first = (uint64_t)blockIdx.x * wpc + warp;
 
-    // ---- producer side of the words ring (lane 0): group pf_g goes to stage pf_stage
+    // ---- producer side of the words ring (lane 0): group pf_g goes to stage pf_stage.  Inside a
+    // point the source pointer just advances by the warp's group stride.
+    const uint32_t ring_s = smem_u32(ring), bar_s = smem_u32(ring_bar);
+    const uint32_t stage_bytes = (uint32_t)b.ring_stage_bytes;
     uint64_t pf_g = g_first;
-    int pf_stage = 0;
-    int pf_p = -1;
-    uint64_t pf_start = 0, pf_end = 0, pf_word_off = 0;
-    uint32_t pf_kp = 0;
+    uint32_t pf_stage = 0;
+    uint64_t pf_end = 0;
+    const uint64_t* pf_ptr = nullptr;
+    uint32_t pf_bytes = 0;
+    uint64_t pf_step = 0;
     auto prefetch_one = [&]() {
         if (pf_g < b.n_groups) {
-            if (pf_p < 0 || pf_g >= pf_end) {
-                pf_p = find_point(b.points, b.n_points, pf_g);
-                const PointDev* pt = &b.points[pf_p];
-                pf_start = pt->group_start;
-                pf_end = pf_p + 1 < b.n_points ? b.points[pf_p + 1].group_start : b.n_groups;
-                pf_word_off = pt->word_off;
-                pf_kp = pt->kp;
+            if (pf_g >= pf_end) {
+                const int pp = find_point(b.points, b.n_points, pf_g);
+                const PointDev* pt = &b.points[pp];
+                pf_end = pp + 1 < b.n_points ? b.points[pp + 1].group_start : b.n_groups;
+                pf_ptr = b.words + pt->word_off + (pf_g - pt->group_start) * pt->kp;
+                pf_bytes = pt->kp * 8u;
+                pf_step = stride * pt->kp;
             }
-            const uint32_t bytes = pf_kp * 8u;
-            mbar_expect_tx(&ring_bar[pf_stage], bytes);
-            bulk_g2s(ring + (size_t)pf_stage * b.ring_stage_bytes, b.words + pf_word_off + (pf_g - pf_start) * pf_kp, bytes,
-                     &ring_bar[pf_stage]);
+            mbar_expect_tx_s(bar_s + pf_stage * 8u, pf_bytes);
+            bulk_g2s_s(ring_s + pf_stage * stage_bytes, pf_ptr, pf_bytes, bar_s + pf_stage * 8u);
+            pf_ptr += pf_step;
         }
         pf_g += stride;
-        pf_stage = pf_stage + 1 == stages ? 0 : pf_stage + 1;
+        pf_stage = pf_stage + 1 == (uint32_t)stages ? 0 : pf_stage + 1;
     };
     if (lane == 0)
         for (int s = 0; s < stages; s++) prefetch_one();
@@ -891,11 +913,54 @@ bcp_kernel(DbDev db, BatchDev b, int warp_bytes) {
         const uint64_t valid = left >= 64 ? ~0ull : ((1ull << left) - 1);
         const uint32_t* code = b.setcode + P_var_off;
         const uint64_t* w = (const uint64_t*)(ring + (size_t)stage * b.ring_stage_bytes);
-        // BCP can only start from a candidate record or a contradicted level-0 value
-        const bool active = !db.unsat && (P_cand_cnt != 0 || (P_flags & POINT_HAS_FIXED) != 0 || b.assign != nullptr);
+        // BCP can only start from a candidate record or a contradicted level-0 value (a set that
+        // covers every live variable also goes the long way: its samples are models)
+        const bool active = !db.unsat && (P_cand_cnt != 0 || (P_flags & POINT_HAS_FIXED) != 0 || b.assign != nullptr ||
+                                          P_n_assumed == (uint32_t)db.n_live);
 
-        if (lane == 0) *c.dead = db.unsat ? valid : 0;
-        mbar_wait(&ring_bar[stage], phase);  // the group's words have landed
+        if (!active) {
+            // ---- streaming path: nothing can be implied or falsified in the groups of this
+            // point.  Each tile is released as soon as it has landed; every sample has the trail
+            // level-0 + assumptions (or is a conflict if the database itself is refuted).  The
+            // loop runs over all groups of this warp inside the point.
+            const uint32_t tr = db.n_base_assigned + P_n_assumed;
+            const uint64_t g_last = P_end - 1;  // the only group of the point that can be ragged
+            const uint32_t n_tail = (uint32_t)(P_n_samples - (g_last - P_start) * 64);
+            const bool want_out = b.conflict_bits != nullptr || b.trail != nullptr;
+            uint32_t cnt = 0;
+            while (true) {
+                mbar_wait_s(bar_s + (uint32_t)stage * 8u, phase);  // the tile has landed (and is not needed)
+                __syncwarp();
+                if (lane == 0) prefetch_one();
+                stage = stage + 1 == stages ? 0 : stage + 1;
+                phase ^= (stage == 0);
+                const uint32_t nv = g == g_last ? n_tail : 64u;
+                cnt += nv;
+                if (want_out) {
+                    const uint64_t vm = nv >= 64 ? ~0ull : ((1ull << nv) - 1);
+                    if (b.conflict_bits && lane == 0) {
+                        b.conflict_bits[g] = db.unsat ? vm : 0ull;
+                        b.full_bits[g] = 0ull;
+                    }
+                    if (b.trail) {
+                        b.trail[g * 64 + lane] = (!db.unsat && ((vm >> lane) & 1ull)) ? tr : 0u;
+                        b.trail[g * 64 + 32 + lane] = (!db.unsat && ((vm >> (lane + 32)) & 1ull)) ? tr : 0u;
+                    }
+                }
+                if (g + stride >= P_end) break;
+                g += stride;
+            }
+            acc.n += cnt;
+            if (db.unsat) {
+                acc.n_conflict += cnt;
+            } else {
+                acc.sum += (uint64_t)cnt * tr;
+                acc.sumsq += (uint64_t)cnt * tr * tr;
+            }
+            continue;
+        }
+        mbar_wait_s(bar_s + (uint32_t)stage * 8u, phase);  // the group's words have landed
+        if (lane == 0) *c.dead = 0;
         __syncwarp();
 
         // ---- (1) assumptions (src_mpi/mpi_predicter.cpp:3236-3242: true bit => positive literal)
