@@ -56,7 +56,13 @@ enum {
     PDSAT_MODE_ENUM = 2,
     /* values supplied by the caller: explicit_values[s*k + j] in {0,1}
      * (te > 0 mode: known states + keystream, src_mpi/mpi_predicter.cpp:3188-3235). */
-    PDSAT_MODE_EXPLICIT = 3
+    PDSAT_MODE_EXPLICIT = 3,
+    /* enumeration of sub-cubes: the samples come in blocks of 2^block_bits (block_bits >= 6);
+     * sample s is assignment index lint = (block_prefix[s >> block_bits] << block_bits)
+     * | (s mod 2^block_bits), bit r of lint = value of set_vars[r] as in PDSAT_MODE_ENUM.
+     * The prefixes of a refuted partial assignment's sub-cube simply do not appear
+     * (BCP-pruned enumeration, src_common/minisat/core/Solver.cc:1380-1423). */
+    PDSAT_MODE_ENUM_BLOCKS = 4
 };
 
 /* One point = one decomposition set and its sample range.  A true value makes the
@@ -70,6 +76,8 @@ typedef struct {
     uint64_t n_samples;
     const uint8_t* explicit_values;  /* EXPLICIT mode only: n_samples * k bytes        */
     uint64_t first_draw;             /* MT19937 mode: draws already consumed (0 = fresh) */
+    const uint64_t* block_prefix;    /* ENUM_BLOCKS mode: n_samples >> block_bits prefixes */
+    int32_t block_bits;
 } pdsat_point;
 
 /* Integer-exact Monte Carlo accumulators of one point: what GetPredict needs
@@ -215,6 +223,34 @@ int pdsat_batch_assign(pdsat_batch* b, int32_t point, uint64_t first, uint64_t n
 int pdsat_batch_models(pdsat_batch* b, int64_t* n_found, int32_t* point_of, uint64_t* sample_of,
                        uint8_t* models);
 void pdsat_batch_destroy(pdsat_batch* b);
+
+/* ---- solve mode: BCP-pruned enumeration of a cube ---------------------------------------
+ * Replaces MPI_Base::MakeAssignsFromMasks (src_mpi/mpi_base.cpp:107-178) + the BCP-decided share
+ * of MPI_Solver::SolverRun (src_mpi/mpi_solver.cpp:167-294) for all 2^k assignments of set_vars
+ * (ascending; bit r of the assignment index lint = value of set_vars[r]), with the traversal
+ * idea of Solver::gen_valid_assumptions_rc2 (Solver.cc:1293-1435): the variables are assigned
+ * from the most significant end in blocks, BCP runs on the device after every block, and a
+ * refuted prefix prunes its whole sub-cube.  The survivors are exactly the assignments whose
+ * full BCP finds no conflict (BCP is monotone), in ascending lint order.
+ * n_fixed_top / fixed_top_value pin the top bits of lint: the task split of
+ * ControlProcessSolve (mpi_solver.cpp:447-473), e.g. rank g of 8 takes n_fixed_top = 3,
+ * fixed_top_value = g. */
+typedef struct {
+    uint64_t n_assignments; /* 2^(k - n_fixed_top)                                         */
+    uint64_t n_conflict;    /* refuted by BCP (pruned sub-cubes included)                  */
+    uint64_t n_models;      /* BCP reached a full assignment without conflict              */
+    uint64_t n_undecided;   /* conflict-free, not full: would go to CDCL                   */
+    uint64_t n_propagated;  /* samples actually propagated on the device                   */
+    uint64_t n_batches;     /* device batches launched                                     */
+} pdsat_enum_stats;
+/* survivors: at most max_survivors assignment indices (models and undecided, ascending) with
+ * is_model flags; stop_at_first_model ends the search at the first model (the reference stops at
+ * the first SAT unless -solve_all, mpi_solver.cpp:285-286; counts are then partial). */
+int pdsat_enumerate(pdsat_db* db, const int32_t* set_vars, int32_t k, int32_t n_fixed_top, uint64_t fixed_top_value,
+                    int32_t stop_at_first_model, uint64_t max_survivors, uint64_t* survivors, uint8_t* is_model,
+                    uint64_t* n_survivors, pdsat_enum_stats* stats);
+/* change the blocks of a single-point ENUM_BLOCKS batch (n_blocks <= the number it was created with) */
+int pdsat_batch_set_blocks(pdsat_batch* b, uint64_t n_blocks, const uint64_t* block_prefix);
 
 /* ---- one-call form (host buffers in, host buffers out; the e2e path) ---------------- */
 int pdsat_eval_batch(pdsat_db* db, int32_t n_points, const pdsat_point* points, pdsat_cost* costs);

@@ -17,7 +17,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libpdsat_b200.so")
 
 PDSAT_OK, PDSAT_ERR_ARG, PDSAT_ERR_CUDA, PDSAT_ERR_UNSAT, PDSAT_ERR_LIMIT = 0, 1, 2, 3, 4
-MODE_MT19937, MODE_COUNTER, MODE_ENUM, MODE_EXPLICIT = 0, 1, 2, 3
+MODE_MT19937, MODE_COUNTER, MODE_ENUM, MODE_EXPLICIT, MODE_ENUM_BLOCKS = 0, 1, 2, 3, 4
 OUT_FLAGS, OUT_TRAIL, OUT_ASSIGN = 1, 2, 4
 COST_WORDS = 8
 
@@ -30,6 +30,7 @@ EXPORTS = [
     "pdsat_batch_assign", "pdsat_batch_models", "pdsat_batch_destroy", "pdsat_eval_batch",
     "pdsat_mt19937_bool_rand", "pdsat_batch_peer_export", "pdsat_batch_peer_connect",
     "pdsat_batch_peer_disconnect", "pdsat_batch_h2d_bytes", "pdsat_db_gates", "pdsat_batch_set_first_draw",
+    "pdsat_enumerate", "pdsat_batch_set_blocks",
 ]
 
 
@@ -42,7 +43,7 @@ class PdsatError(RuntimeError):
 class CPoint(C.Structure):
     _fields_ = [("set_vars", C.c_void_p), ("k", C.c_int32), ("mode", C.c_int32), ("seed", C.c_uint64),
                 ("first_sample", C.c_uint64), ("n_samples", C.c_uint64), ("explicit_values", C.c_void_p),
-                ("first_draw", C.c_uint64)]
+                ("first_draw", C.c_uint64), ("block_prefix", C.c_void_p), ("block_bits", C.c_int32)]
 
 
 class CCost(C.Structure):
@@ -57,6 +58,11 @@ class CDbInfo(C.Structure):
                 ("max_clause_len", C.c_int32), ("status", C.c_int32), ("warps_per_cta", C.c_int32),
                 ("smem_bytes", C.c_int32), ("grid", C.c_int32), ("db_in_smem", C.c_int32), ("sm_count", C.c_int32),
                 ("n_gates", C.c_int32), ("blob_bytes", C.c_int32), ("n_gate_clauses", C.c_int64)]
+
+
+class CEnumStats(C.Structure):
+    _fields_ = [("n_assignments", C.c_uint64), ("n_conflict", C.c_uint64), ("n_models", C.c_uint64),
+                ("n_undecided", C.c_uint64), ("n_propagated", C.c_uint64), ("n_batches", C.c_uint64)]
 
 
 class CGate(C.Structure):
@@ -110,6 +116,9 @@ def lib():
     L.pdsat_batch_h2d_bytes.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
     L.pdsat_db_gates.argtypes = [C.c_void_p, C.c_int32, C.POINTER(CGate), C.POINTER(C.c_int32)]
     L.pdsat_batch_set_first_draw.argtypes = [C.c_void_p, C.c_int32, C.c_uint64]
+    L.pdsat_enumerate.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_uint64, C.c_int32, C.c_uint64,
+                                  C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(CEnumStats)]
+    L.pdsat_batch_set_blocks.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p]
     _lib = L
     return L
 
@@ -135,6 +144,8 @@ class Point:
     first_sample: int = 0
     explicit_values: Optional[np.ndarray] = None  # [n_samples, k] of {0,1}
     first_draw: int = 0  # MT19937: draws the worker's generator has already made
+    block_prefix: Optional[np.ndarray] = None  # ENUM_BLOCKS: one uint64 prefix per block
+    block_bits: int = 0
 
 
 @dataclass
@@ -162,6 +173,12 @@ def _cpoints(points: Sequence[Point]):
         arr[i].first_sample = p.first_sample
         arr[i].n_samples = p.n_samples
         arr[i].first_draw = p.first_draw
+        arr[i].block_prefix = None
+        arr[i].block_bits = p.block_bits
+        if p.block_prefix is not None:
+            bp = np.ascontiguousarray(p.block_prefix, dtype=np.uint64)
+            keep.append(bp)
+            arr[i].block_prefix = bp.ctypes.data
         if p.explicit_values is not None:
             ev = np.ascontiguousarray(p.explicit_values, dtype=np.uint8)
             assert ev.size == p.n_samples * len(sv)
@@ -219,6 +236,21 @@ class ClauseDb:
 
     def set_stream(self, stream_ptr: int) -> None:
         _check(lib().pdsat_set_stream(self.h, C.c_void_p(stream_ptr)))
+
+    def enumerate(self, set_vars: Sequence[int], n_fixed_top: int = 0, fixed_top_value: int = 0,
+                  stop_at_first_model: bool = False, max_survivors: int = 1 << 20):
+        """BCP-pruned enumeration of the cube over set_vars (ascending): returns
+        (survivor indices, is_model flags, CEnumStats)."""
+        sv = np.ascontiguousarray(set_vars, dtype=np.int32)
+        surv = np.zeros(max(max_survivors, 1), dtype=np.uint64)
+        ism = np.zeros(max(max_survivors, 1), dtype=np.uint8)
+        ns = C.c_uint64(0)
+        st = CEnumStats()
+        _check(lib().pdsat_enumerate(self.h, sv.ctypes.data, len(sv), n_fixed_top, fixed_top_value,
+                                     1 if stop_at_first_model else 0, max_survivors, surv.ctypes.data, ism.ctypes.data,
+                                     C.byref(ns), C.byref(st)))
+        n = min(ns.value, max_survivors)
+        return surv[:n].copy(), ism[:n].astype(bool), st
 
     def eval_batch(self, points: Sequence[Point]) -> List[Cost]:
         """One call, host buffers in / out (pdsat_eval_batch): the e2e path."""

@@ -55,6 +55,9 @@ struct PointDev {
     uint32_t cand_cnt;
     uint32_t kp;              // words per group in `words`: k rounded up to even (16-byte tiles)
     uint32_t flags;           // POINT_*
+    uint64_t block_off;       // ENUM_BLOCKS: first prefix of this point in block_prefix
+    uint32_t block_bits;
+    uint32_t pad_;
 };
 static constexpr uint32_t POINT_HAS_FIXED = 1u;  // some set variable is assigned at level 0
 
@@ -86,6 +89,7 @@ struct BatchDev {
     const uint4* cand;          // first-wave candidate clause records, all points
     uint64_t* words;
     const uint32_t* stream;
+    const uint64_t* block_prefix;  // ENUM_BLOCKS prefixes, all points
     unsigned long long* cost;   // n_points * 8
     uint64_t* conflict_bits;    // per global group (optional)
     uint64_t* full_bits;        // per global group (optional)
@@ -145,8 +149,10 @@ __global__ void fill_words_kernel(BatchDev b) {
     } else if (pt.mode == 1) {  // PDSAT_MODE_RANDOM_COUNTER
         uint64_t g = pt.first_sample / 64 + gi;
         out = splitmix64(pt.seed + 0x9E3779B97F4A7C15ull * (g * 65536ull + j + 1));
-    } else if (pt.mode == 2) {  // PDSAT_MODE_ENUM
+    } else if (pt.mode == 2 || pt.mode == 4) {  // PDSAT_MODE_ENUM / PDSAT_MODE_ENUM_BLOCKS
         uint64_t lint = pt.first_sample + s0;
+        if (pt.mode == 4)  // blocks of >= 64 samples: the 64 samples of a group share their prefix
+            lint = (b.block_prefix[pt.block_off + (s0 >> pt.block_bits)] << pt.block_bits) | (s0 & ((1ull << pt.block_bits) - 1));
         if (j < 64) {
 #pragma unroll 8
             for (int s = 0; s < 64; s++) out |= (((lint + s) >> j) & 1ull) << s;

@@ -64,7 +64,8 @@ struct HostPoint {
     std::vector<uint32_t> setcode;
     int32_t mode = 0;
     uint64_t seed = 0, first_sample = 0, n_samples = 0, first_draw = 0;
-    uint32_t kp = 0, flags = 0;
+    uint32_t kp = 0, flags = 0, block_bits = 0;
+    uint64_t block_off = 0, block_cap = 0;  // ENUM_BLOCKS: offset / capacity in the prefix buffer
     uint64_t n_groups = 0, group_start = 0, word_off = 0, stream_off = 0, stream_skip = 0, stream_words = 0;
     uint64_t mt_first_round = 0, mt_rounds = 0;
     uint32_t n_assumed_live = 0;
@@ -116,6 +117,10 @@ struct pdsat_batch {
     // explicit values, packed on the host (pinned)
     uint32_t* h_stream = nullptr;
     bool has_explicit = false;
+    // ENUM_BLOCKS prefixes (pinned staging + device)
+    uint64_t* h_blocks = nullptr;
+    uint64_t* d_blocks = nullptr;
+    uint64_t n_blocks_total = 0;
     PointDev* h_points = nullptr;  // pinned mirror
     // fused peer reduce (multi-GPU)
     unsigned long long* d_peer_own = nullptr;          // this rank's IPC-exported buffer
@@ -419,8 +424,10 @@ int pdsat_batch_create(pdsat_db* db, int32_t n_points, const pdsat_point* points
     for (int p = 0; p < n_points; p++) {
         const pdsat_point& in = points[p];
         HostPoint& hp = b->pts[p];
-        if (in.k <= 0 || !in.set_vars || in.n_samples == 0 || in.mode < 0 || in.mode > 3 ||
+        if (in.k <= 0 || !in.set_vars || in.n_samples == 0 || in.mode < 0 || in.mode > 4 ||
             (in.mode == PDSAT_MODE_EXPLICIT && !in.explicit_values) ||
+            (in.mode == PDSAT_MODE_ENUM_BLOCKS && (!in.block_prefix || in.block_bits < 6 || in.block_bits > 62 ||
+                                                  (in.n_samples & ((1ull << in.block_bits) - 1)))) ||
             (in.mode == PDSAT_MODE_RANDOM_COUNTER && (in.first_sample & 63))) {
             pdsat_batch_destroy(b);
             return fail(PDSAT_ERR_ARG, "pdsat_batch_create: bad point " + std::to_string(p));
@@ -515,6 +522,11 @@ int pdsat_batch_create(pdsat_db* db, int32_t n_points, const pdsat_point* points
             hp.stream_skip = 0;
             hp.stream_words = (in.n_samples * (uint64_t)in.k + 31) / 32;
             b->has_explicit = true;
+        } else if (in.mode == PDSAT_MODE_ENUM_BLOCKS) {
+            hp.block_bits = (uint32_t)in.block_bits;
+            hp.block_cap = in.n_samples >> in.block_bits;
+            hp.block_off = b->n_blocks_total;
+            b->n_blocks_total += hp.block_cap;
         }
         n_codes += (size_t)in.k;
     }
@@ -604,6 +616,13 @@ int pdsat_batch_create(pdsat_db* db, int32_t n_points, const pdsat_point* points
         CUB(cudaMemcpy(b->d_mt_segs, b->h_mt_segs, sizeof(MtSegment) * b->n_mt_segs, cudaMemcpyHostToDevice));
         CUB(cudaFuncSetAttribute(mt19937_jump_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MT_JUMP_SMEM));
     }
+    if (b->n_blocks_total) {
+        CUB(cudaMalloc(&b->d_blocks, sizeof(uint64_t) * b->n_blocks_total));
+        CUB(cudaMallocHost(&b->h_blocks, sizeof(uint64_t) * b->n_blocks_total));
+        for (int p = 0; p < n_points; p++)
+            if (b->pts[p].mode == PDSAT_MODE_ENUM_BLOCKS)
+                memcpy(b->h_blocks + b->pts[p].block_off, points[p].block_prefix, sizeof(uint64_t) * b->pts[p].block_cap);
+    }
     if (b->has_explicit) {
         CUB(cudaMallocHost(&b->h_stream, sizeof(uint32_t) * stream_words));
         memset(b->h_stream, 0, sizeof(uint32_t) * stream_words);
@@ -639,6 +658,9 @@ int pdsat_batch_create(pdsat_db* db, int32_t n_points, const pdsat_point* points
             pd.cand_cnt = (uint32_t)(hp.cand.size() + hp.gcand.size());
             pd.kp = hp.kp;
             pd.flags = hp.flags;
+            pd.block_off = hp.block_off;
+            pd.block_bits = hp.block_bits;
+            pd.pad_ = 0;
             off += pd.k;
             codes.insert(codes.end(), hp.setcode.begin(), hp.setcode.end());
             if (pd.cand_cnt) {  // gates first, then clauses: neighbouring lanes take the same path
@@ -829,6 +851,10 @@ int pdsat_batch_fill(pdsat_batch* b) {
             h2d += (int64_t)(sizeof(uint32_t) * hp.stream_words);
         }
     }
+    if (b->n_blocks_total) {
+        CU(cudaMemcpyAsync(b->d_blocks, b->h_blocks, sizeof(uint64_t) * b->n_blocks_total, cudaMemcpyHostToDevice, st));
+        h2d += (int64_t)(sizeof(uint64_t) * b->n_blocks_total);
+    }
     CU(cudaEventRecord(b->ev_h2d, st));
     b->h2d_pending = true;
     BatchDev bd{};
@@ -838,6 +864,7 @@ int pdsat_batch_fill(pdsat_batch* b) {
     bd.n_words = b->n_words;
     bd.words = b->d_words;
     bd.stream = b->d_stream;
+    bd.block_prefix = b->d_blocks;
     const int threads = 256;
     const uint64_t blocks = (b->n_words + threads - 1) / threads;
     fill_words_kernel<<<(unsigned)blocks, threads, 0, st>>>(bd);
@@ -1122,6 +1149,8 @@ void pdsat_batch_destroy(pdsat_batch* b) {
     cudaFree(b->d_mt_states);
     cudaFree(b->d_mt_segs);
     cudaFree(b->d_mt_tasks);
+    cudaFree(b->d_blocks);
+    if (b->h_blocks) cudaFreeHost(b->h_blocks);
     if (b->h_mt_tasks) cudaFreeHost(b->h_mt_tasks);
     if (b->h_mt_states) cudaFreeHost(b->h_mt_states);
     if (b->h_mt_segs) cudaFreeHost(b->h_mt_segs);
@@ -1136,6 +1165,201 @@ void pdsat_batch_destroy(pdsat_batch* b) {
         db->zombie = false;
         pdsat_destroy(db);
     }
+}
+
+int pdsat_batch_set_blocks(pdsat_batch* b, uint64_t n_blocks, const uint64_t* block_prefix) {
+    if (!b || !block_prefix || n_blocks == 0 || b->pts.size() != 1 || b->pts[0].mode != PDSAT_MODE_ENUM_BLOCKS ||
+        n_blocks > b->pts[0].block_cap)
+        return fail(PDSAT_ERR_ARG, "pdsat_batch_set_blocks: needs a single-point ENUM_BLOCKS batch and n_blocks within its capacity");
+    staging_wait(b);
+    HostPoint& hp = b->pts[0];
+    memcpy(b->h_blocks, block_prefix, sizeof(uint64_t) * n_blocks);
+    hp.n_samples = n_blocks << hp.block_bits;
+    hp.n_groups = hp.n_samples / 64;
+    b->h_points[0].n_samples = hp.n_samples;
+    b->n_groups = hp.n_groups;
+    b->n_words = hp.n_groups * (uint64_t)hp.kp;
+    b->filled = false;
+    return PDSAT_OK;
+}
+
+// ---- BCP-pruned enumeration (see pdsat_cuda.h).  Depth-first over chunks of surviving prefixes;
+// one reusable single-point ENUM_BLOCKS batch per level.
+namespace {
+struct EnumLevel {
+    int depth_before = 0;  // bits of lint fixed by the prefixes fed to this level
+    int w = 0;             // bits this level enumerates
+    uint64_t cap_blocks = 0;
+    pdsat_batch* b = nullptr;
+    std::vector<uint64_t> conflict, full;  // flag words of the last run
+};
+}  // namespace
+
+int pdsat_enumerate(pdsat_db* db, const int32_t* set_vars, int32_t k, int32_t n_fixed_top, uint64_t fixed_top_value,
+                    int32_t stop_at_first_model, uint64_t max_survivors, uint64_t* survivors, uint8_t* is_model,
+                    uint64_t* n_survivors, pdsat_enum_stats* stats) {
+    int rc = need_device(db);
+    if (rc) return rc;
+    if (!set_vars || k <= 0 || k > 62 || n_fixed_top < 0 || n_fixed_top >= k || !stats ||
+        (n_fixed_top < 64 && n_fixed_top > 0 && (fixed_top_value >> n_fixed_top)) || (n_fixed_top == 0 && fixed_top_value))
+        return fail(PDSAT_ERR_ARG, "pdsat_enumerate: bad argument");
+    for (int i = 1; i < k; i++)
+        if (set_vars[i] <= set_vars[i - 1]) return fail(PDSAT_ERR_ARG, "pdsat_enumerate: set_vars must be ascending");
+    memset(stats, 0, sizeof(*stats));
+    if (n_survivors) *n_survivors = 0;
+    const int kf = k - n_fixed_top;
+    stats->n_assignments = 1ull << kf;
+    // level widths: the first level takes up to 16 free bits at once, the following ones 8 (never
+    // fewer than 6: a block is at least one 64-sample group), the last one what is left
+    std::vector<EnumLevel> lv;
+    {
+        int left = kf, depth = n_fixed_top;
+        while (left > 0) {
+            int w = lv.empty() ? 16 : 8;
+            if (w > left) w = left;
+            if (left - w > 0 && left - w < 6) w = left;  // do not leave a sliver for the last level
+            if (w < 6) {  // tiny cubes: pad the enumeration with variables from the fixed top (w >= 6 required)
+                if (lv.empty()) break;
+                lv.back().w += w;
+                left -= w;
+                continue;
+            }
+            EnumLevel L;
+            L.depth_before = depth;
+            L.w = w;
+            lv.push_back(L);
+            depth += w;
+            left -= w;
+        }
+    }
+    auto cleanup = [&]() {
+        for (auto& L : lv)
+            if (L.b) pdsat_batch_destroy(L.b);
+    };
+    if (lv.empty()) {
+        // fewer than 6 free bits: one plain ENUM batch over the whole (tiny) cube
+        const uint64_t n = 1ull << kf;
+        pdsat_point pt{};
+        pt.set_vars = set_vars;
+        pt.k = k;
+        pt.mode = PDSAT_MODE_ENUM;
+        pt.first_sample = fixed_top_value << kf;
+        pt.n_samples = n;
+        pdsat_batch* b = nullptr;
+        if ((rc = pdsat_batch_create(db, 1, &pt, PDSAT_OUT_FLAGS, 0, &b))) return rc;
+        uint64_t cw = 0, fw = 0;
+        pdsat_cost c;
+        rc = pdsat_batch_fill(b);
+        if (!rc) rc = pdsat_batch_propagate(b);
+        if (!rc) rc = pdsat_batch_costs(b, &c);
+        if (!rc) rc = pdsat_batch_flags(b, 0, &cw, &fw);
+        pdsat_batch_destroy(b);
+        if (rc) return rc;
+        stats->n_propagated = n;
+        stats->n_batches = 1;
+        uint64_t ns = 0;
+        for (uint64_t s = 0; s < n; s++) {
+            if ((cw >> s) & 1) continue;
+            const bool model = (fw >> s) & 1;
+            if (model) stats->n_models++;
+            else stats->n_undecided++;
+            if (ns < max_survivors && survivors) {
+                survivors[ns] = (fixed_top_value << kf) | s;
+                if (is_model) is_model[ns] = model;
+            }
+            ns++;
+        }
+        stats->n_conflict = n - stats->n_models - stats->n_undecided;
+        if (n_survivors) *n_survivors = ns;
+        return PDSAT_OK;
+    }
+    const uint64_t cap_samples = 1ull << 24;
+    for (auto& L : lv) {
+        L.cap_blocks = cap_samples >> L.w;
+        if (L.cap_blocks < 1) L.cap_blocks = 1;
+        // the level's set: the top depth_before + w variables (ascending = low bits first)
+        const int d = L.depth_before + L.w;
+        std::vector<uint64_t> zero(L.cap_blocks, 0);
+        pdsat_point pt{};
+        pt.set_vars = set_vars + (k - d);
+        pt.k = d;
+        pt.mode = PDSAT_MODE_ENUM_BLOCKS;
+        pt.n_samples = L.cap_blocks << L.w;
+        pt.block_prefix = zero.data();
+        pt.block_bits = L.w;
+        if ((rc = pdsat_batch_create(db, 1, &pt, PDSAT_OUT_FLAGS, 0, &L.b))) {
+            cleanup();
+            return rc;
+        }
+        L.conflict.resize((size_t)(pt.n_samples / 64));
+        L.full.resize((size_t)(pt.n_samples / 64));
+    }
+    // explicit stack of (level, prefixes); chunks are pushed in reverse so that leaves come out
+    // in ascending order
+    struct Item {
+        int level;
+        std::vector<uint64_t> prefixes;
+    };
+    std::vector<Item> stack;
+    stack.push_back(Item{0, {fixed_top_value}});
+    uint64_t ns = 0;
+    bool stop = false;
+    const int last = (int)lv.size() - 1;
+    while (!stack.empty() && !stop) {
+        Item it = std::move(stack.back());
+        stack.pop_back();
+        EnumLevel& L = lv[it.level];
+        const uint64_t nb = it.prefixes.size();
+        if ((rc = pdsat_batch_set_blocks(L.b, nb, it.prefixes.data())) || (rc = pdsat_batch_fill(L.b)) ||
+            (rc = pdsat_batch_propagate(L.b)) || (rc = pdsat_batch_flags(L.b, 0, L.conflict.data(), L.full.data()))) {
+            cleanup();
+            return rc;
+        }
+        stats->n_batches++;
+        stats->n_propagated += nb << L.w;
+        const uint64_t per_block_words = (1ull << L.w) / 64;
+        std::vector<uint64_t> next;
+        for (uint64_t blk = 0; blk < nb && !stop; blk++) {
+            const uint64_t base = it.prefixes[blk] << L.w;
+            for (uint64_t wi = 0; wi < per_block_words && !stop; wi++) {
+                const uint64_t cw = L.conflict[blk * per_block_words + wi], fw = L.full[blk * per_block_words + wi];
+                uint64_t alive = ~cw;
+                while (alive) {
+                    const int bit = __builtin_ctzll(alive);
+                    alive &= alive - 1;
+                    const uint64_t v = base | (wi * 64 + (uint64_t)bit);
+                    if (it.level < last) {
+                        next.push_back(v);
+                    } else {
+                        const bool model = (fw >> bit) & 1;
+                        if (model) stats->n_models++;
+                        else stats->n_undecided++;
+                        if (ns < max_survivors && survivors) {
+                            survivors[ns] = v;
+                            if (is_model) is_model[ns] = model;
+                        }
+                        ns++;
+                        if (model && stop_at_first_model) {
+                            stop = true;
+                            break;
+                        }
+                    }
+                }
+            }
+        }
+        if (it.level < last && !next.empty()) {
+            const uint64_t cap = lv[it.level + 1].cap_blocks;
+            const uint64_t n_chunks = (next.size() + cap - 1) / cap;
+            for (uint64_t ch = n_chunks; ch-- > 0;) {
+                const uint64_t lo = ch * cap, hi = std::min<uint64_t>(next.size(), lo + cap);
+                stack.push_back(Item{it.level + 1, std::vector<uint64_t>(next.begin() + lo, next.begin() + hi)});
+            }
+        }
+    }
+    cleanup();
+    if (!stop) stats->n_conflict = stats->n_assignments - stats->n_models - stats->n_undecided;
+    if (n_survivors) *n_survivors = ns;
+    return PDSAT_OK;
 }
 
 int pdsat_eval_batch(pdsat_db* db, int32_t n_points, const pdsat_point* points, pdsat_cost* costs) {
