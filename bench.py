@@ -294,6 +294,178 @@ def work_equivalent_bytes(nv, clauses, stream, set_vars, seed, n_probe=400):
     return tot / cnt if cnt else None
 
 
+def _cpu_enum_worker(args):
+    kind, n_known, first, n = args
+    from oracle import oracle as orc
+    from pdsat_b200 import fixtures as fx
+    key = ("a52", kind, n_known)
+    if key not in _CPU:
+        nv, cl, fixed, dset, secret = fx.a5_2_weakened_instance(n_known)
+        offs, lits = fx.to_csr(cl)
+        O = orc.Oracle(nv, offs, lits, kind)
+        O.add_units(fixed)
+        _CPU[key] = (O, dset)
+    O, dset = _CPU[key]
+    t0 = time.perf_counter()
+    conflict, full, sums = O.batch_enum(dset, first, n)
+    return time.perf_counter() - t0, sums, np.packbits(conflict, bitorder="little"), np.packbits(full, bitorder="little")
+
+
+def leg_tabu(api, torch, dist, db, rank, world, args):
+    """BASELINE config 3: one tabu step = the centre {148..177} and its 177 Hamming-1 neighbours
+    (src_mpi/mpi_predicter.cpp:2770, 2926-2935), tabu_samples mt19937 samples per point (stream
+    seed = 1 + point), every point's sample range sharded over the ranks, ONE reduce of the 178 x 8
+    accumulators fused into the BCP kernel over NVLink.  Timed end to end through the public call
+    sequence; the all-rank sums must equal an un-sharded evaluation on rank 0, integer for integer."""
+    from pdsat_b200 import predicter as pr
+    sets = [SET_VARS] + pr.hamming1_neighbourhood(SET_VARS, list(range(1, 178)))
+    n_pt = args.tabu_samples
+    lo, hi = pr.shard_range(n_pt, rank, world)
+    batch = api.Batch(db, [api.Point(sv, hi - lo, api.MODE_MT19937, seed=1 + i, first_sample=lo)
+                           for i, sv in enumerate(sets)])
+    mode = "none"
+    cost_t = None
+    if dist is not None:
+        cost_t = torch.zeros(api.COST_WORDS * len(sets), dtype=torch.int64, device="cuda")
+        batch.set_cost_buffer(cost_t.data_ptr())
+        mode = connect_peers(torch, dist, batch, rank, world, args.reduce)
+
+    def step():
+        batch.fill()
+        batch.propagate()
+        if mode == "nccl":
+            dist.all_reduce(cost_t)
+        return batch.costs()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(2):
+        step()
+    barrier()
+    reps = 3
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        costs = step()
+    barrier()
+    dt = (time.perf_counter() - t0) / reps
+    f_ms, p_ms = batch.last_ms()
+    t = torch.tensor([dt, f_ms, p_ms], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.barrier()
+    dt, f_ms, p_ms = (float(x) for x in t.tolist())
+    batch.close()
+    out = None
+    if rank == 0:
+        got = [[c.n, c.n_conflict, c.n_full, c.sum_trail, c.sumsq_trail, c.n_implied_any] for c in costs]
+        identical = None
+        if world > 1:  # the same step un-sharded on this GPU alone
+            whole = db.eval_batch([api.Point(sv, n_pt, api.MODE_MT19937, seed=1 + i) for i, sv in enumerate(sets)])
+            identical = got == [[c.n, c.n_conflict, c.n_full, c.sum_trail, c.sumsq_trail, c.n_implied_any] for c in whole]
+        est = [pr.predict_from_cost(c, len(sv), "prep") for c, sv in zip(costs, sets)]
+        out = {"points": len(sets), "samples_per_point": n_pt, "ranks": world, "reduce": mode,
+               "e2e_ms_per_step": dt * 1e3, "fill_ms": f_ms, "propagate_ms": p_ms,
+               "samples_per_s_e2e": len(sets) * n_pt / dt, "points_per_s": len(sets) / dt,
+               "all_points_complete": all(g[0] == n_pt for g in got),
+               "bit_identical_to_one_gpu": identical,
+               "sum_check": [sum(g[j] for g in got) for j in range(6)],
+               "best_prep_estimate_finite": bool(any(float(e[2]) < 1e300 for e in est))}
+    return out
+
+
+def leg_solve(api, torch, dist, rank, world, args):
+    """BASELINE config 4: generated A5/2 CNF, keystream + R4 + 32 state bits known, solve-mode
+    enumeration of all 2^32 assignments of the other 32 state variables.  Rank g owns the
+    assignments whose top log2(N) index bits equal g (task split of mpi_solver.cpp:447-473);
+    BCP-pruned enumeration on the device (pdsat_enumerate); then allreduce(max) of the found flag
+    and allgather of the hit indices.  Rank 0 also checks a 2^20 slice around the secret against
+    the reference BCP on the host cores (conflict / model flags of every assignment)."""
+    from pdsat_b200 import fixtures as fx
+    nv, cl, fixed, dset, secret = fx.a5_2_weakened_instance(args.a52_known)
+    offs, lits = fx.to_csr(cl)
+    t0 = time.perf_counter()
+    db = api.ClauseDb(nv, offs, lits, device=torch.cuda.current_device())
+    db.set_fixed_assumptions(fixed)
+    upload_s = time.perf_counter() - t0
+    k = len(dset)
+    top = world.bit_length() - 1
+    assert (1 << top) == world, "solve leg needs a power-of-two number of ranks"
+    idx = sum(int(secret[v - 1]) << r for r, v in enumerate(dset))
+    db.enumerate(dset[-8:], max_survivors=16)  # warm-up (module load, allocations)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    barrier()
+    t0 = time.perf_counter()
+    surv, ism, st = db.enumerate(dset, n_fixed_top=top, fixed_top_value=rank, max_survivors=1 << 12)
+    hits = torch.full((16,), -1, dtype=torch.int64, device="cuda")
+    models = [int(x) for x, m in zip(surv, ism) if m][:16]
+    if models:
+        hits[:len(models)] = torch.tensor(models, dtype=torch.int64, device="cuda")
+    found = torch.tensor([1 if models else 0], device="cuda")
+    stats = torch.tensor([st.n_conflict, st.n_models, st.n_undecided, st.n_propagated, st.n_batches], dtype=torch.int64,
+                         device="cuda")
+    all_hits = [hits]
+    if dist is not None:
+        dist.all_reduce(found, op=dist.ReduceOp.MAX)   # found flag
+        all_hits = [torch.empty_like(hits) for _ in range(world)]
+        dist.all_gather(all_hits, hits)                # the (rare) satisfying assignment indices
+        dist.all_reduce(stats)
+    barrier()
+    dt = time.perf_counter() - t0
+    tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    dt = float(tt.item())
+    out = None
+    if rank == 0:
+        gathered = sorted(int(x) for h in all_hits for x in h.tolist() if x >= 0)
+        n_conf, n_mod, n_und, n_prop, n_bat = (int(x) for x in stats.tolist())
+        info = db.info()
+        # device brute force on a 2^20 slice around the secret vs the reference BCP on the host cores
+        sl = args.solve_check_bits
+        first = (idx >> sl) << sl
+        b = api.Batch(db, [api.Point(dset, 1 << sl, api.MODE_ENUM, first_sample=first)], api.OUT_FLAGS)
+        for _ in range(2):
+            c = b.run()[0]
+        f_ms, p_ms = b.last_ms()
+        conflict, full = b.flags(0)
+        b.close()
+        cores = os.cpu_count() or 1
+        cuts = [first + (1 << sl) * i // cores for i in range(cores + 1)]
+        res = cpu_pool().map(_cpu_enum_worker, [(cpu_kind(), args.a52_known, cuts[i], cuts[i + 1] - cuts[i])
+                                                for i in range(cores)])
+        cpu_conf = np.concatenate([np.unpackbits(r[2], bitorder="little")[:cuts[i + 1] - cuts[i]] for i, r in enumerate(res)]).astype(bool)
+        cpu_full = np.concatenate([np.unpackbits(r[3], bitorder="little")[:cuts[i + 1] - cuts[i]] for i, r in enumerate(res)]).astype(bool)
+        cpu_rate = (1 << sl) / max(r[0] for r in res)
+        out = {"instance": "A5/2 (generated), %d vars / %d clauses, keystream %d + R4 + %d state bits known" %
+                           (nv, len(cl), 114, args.a52_known),
+               "set_size": k, "assignments": 1 << k, "ranks": world, "upload_s": upload_s,
+               "live_vars": info.n_live_vars, "gates": info.n_gates, "warps_per_cta": info.warps_per_cta,
+               "seconds": dt, "assignments_per_s": (1 << k) / dt,
+               "found_flag": int(found.item()), "hit_indices": gathered, "secret_index": idx,
+               "secret_found": idx in gathered,
+               "conflicts": n_conf, "models": n_mod, "undecided": n_und,
+               "all_decided": n_conf + n_mod + n_und == (1 << k),
+               "samples_propagated": n_prop, "device_batches": n_bat,
+               "pruning": "BCP after every block of assigned variables; %.2e of the cube is ever propagated" % (n_prop / (1 << k)),
+               "slice_check": {"bits": sl, "first": first, "device_brute_force_assignments_per_s": (1 << sl) / ((f_ms + p_ms) * 1e-3),
+                               "conflict_mismatches": int((conflict != cpu_conf).sum()),
+                               "model_mismatches": int((full != cpu_full).sum()),
+                               "cpu_assignments_per_s": cpu_rate, "cpu_cores": cores,
+                               "cpu_brute_force_2^%d_hours" % k: (1 << k) / cpu_rate / 3600.0}}
+    if dist is not None:
+        dist.barrier()
+    db.close()
+    return out
+
+
 def load_profile_metrics():
     tp = os.path.join(ROOT, "profiles", "bcp_kernel_metrics.json")
     return json.load(open(tp)) if os.path.exists(tp) else {}
@@ -469,6 +641,14 @@ def run_ours(args):
                      "ncu": prof.get("k%d" % k)}
             cascade["k%d" % k] = entry
         extra["cascade"] = cascade
+    # ---------------- configs 3 and 4 at every N (collective legs: all ranks take part)
+    if not args.no_extra:
+        extra_tabu = leg_tabu(api, torch, dist, db, rank, world, args)
+        extra_solve = leg_solve(api, torch, dist, rank, world, args)
+        torch.cuda.set_stream(stream_t)
+        if rank == 0:
+            extra["tabu_step"] = extra_tabu
+            extra["solve_a52"] = extra_solve
 
     t = torch.tensor([dev_ms, e2e_s * 1e3, float(kernel_ms)], dtype=torch.float64, device="cuda")
     if dist is not None:
@@ -569,6 +749,14 @@ def connect_peers(torch, dist, batch, rank, world, want):
     return mode
 
 
+def close_pool():
+    global _POOL
+    if _POOL is not None:
+        _POOL.close()
+        _POOL.join()
+        _POOL = None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -582,16 +770,22 @@ def main():
     ap.add_argument("--cascade", type=lambda v: [int(x) for x in v.split(",") if x], default=[86, 90, 100, 120, 177],
                     help="set sizes (bivium_Ending2 prefixes) of the timed + parity-checked cascade legs")
     ap.add_argument("--cascade-samples", type=int, default=1_000_000)
+    ap.add_argument("--tabu-samples", type=int, default=1_000_000, help="samples per point of the tabu-step leg")
+    ap.add_argument("--a52-known", type=int, default=32, help="known R1|R2|R3 bits of the A5/2 solve leg (set = 64 - known)")
+    ap.add_argument("--solve-check-bits", type=int, default=18, help="log2 size of the slice checked against the CPU")
     ap.add_argument("--reduce", default="auto", choices=["auto", "peer", "nccl"],
                     help="N > 1: fused NVLink peer-memory reduce (auto/peer; falls back to NCCL if CUDA IPC "
                          "is unavailable) or the separate NCCL all-reduce (DESIGN.md section 6)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_ours(args)
+    try:
+        if args.impl == "reference":
+            run_reference(args)
+        else:
+            run_ours(args)
+    finally:
+        close_pool()
 
 
 if __name__ == "__main__":

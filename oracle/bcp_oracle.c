@@ -474,6 +474,29 @@ void orc_batch_mt(void* hv, int mode, uint32_t seed, const int32_t* set_vars, in
     free(a);
 }
 
+/* Batch form of the solve-mode enumeration (mpi_base.cpp:148-169 order): assignment indices
+ * first .. first+n-1 over vars_sorted, BCP only on the persistent DB.  Same outputs as
+ * orc_batch_mt. */
+void orc_batch_enum(void* hv, const int32_t* vars_sorted, int k, uint64_t first, uint64_t n, uint64_t* conflict_bits,
+                    uint64_t* full_bits, uint64_t* sums) {
+    int32_t* a = (int32_t*)malloc(sizeof(int32_t) * (size_t)(k + 1));
+    for (uint64_t s = 0; s < n; s++) {
+        const uint64_t lint = first + s;
+        for (int r = 0; r < k; r++) a[r] = 2 * (vars_sorted[r] - 1) + (((lint >> r) & 1) ? 0 : 1);
+        orc_result r;
+        orc_bcp(hv, a, k, &r, NULL);
+        if (conflict_bits && r.conflict) conflict_bits[s >> 6] |= 1ull << (s & 63);
+        if (full_bits && r.full) full_bits[s >> 6] |= 1ull << (s & 63);
+        if (sums) {
+            sums[0] += (uint64_t)r.conflict;
+            sums[1] += (uint64_t)r.full;
+            sums[4] += r.propagations;
+            sums[5] += r.watch_scans;
+        }
+    }
+    free(a);
+}
+
 /* ---------------------------------------------------------------- enumeration order
  * src_mpi/mpi_base.cpp:107-178 MakeAssignsFromMasks: bit r of lint <-> r-th variable
  * (ascending var index) of the variate part; set bit => positive literal. */

@@ -59,6 +59,9 @@ def _lib(kind: str):
     L.orc_batch_mt.restype = None
     L.orc_batch_mt.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_uint64,
                                C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.orc_batch_enum.restype = None
+    L.orc_batch_enum.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p,
+                                 C.c_void_p]
     if kind == "port":
         L.orc_mt19937_draws.argtypes = [C.c_uint32, C.c_uint64, C.c_uint64, C.c_void_p]
         L.orc_bool_rand.argtypes = [C.c_uint32, C.c_uint64, C.c_uint64, C.c_void_p]
@@ -141,6 +144,19 @@ class Oracle:
         conflict = np.unpackbits(cb.view(np.uint8), bitorder="little")[:n].astype(bool)
         full = np.unpackbits(fb.view(np.uint8), bitorder="little")[:n].astype(bool)
         return conflict, full, tr, [int(x) for x in sums]
+
+    def batch_enum(self, vars_sorted: Sequence[int], first: int, n: int):
+        """Assignment indices first..first+n-1 (MakeAssignsFromMasks order), BCP only, looped in C:
+        (conflict[n] bool, full[n] bool, sums)."""
+        sv = np.ascontiguousarray(vars_sorted, dtype=np.int32)
+        g = (n + 63) // 64
+        cb = np.zeros(g, dtype=np.uint64)
+        fb = np.zeros(g, dtype=np.uint64)
+        sums = np.zeros(6, dtype=np.uint64)
+        self.L.orc_batch_enum(self.h, sv.ctypes.data, len(sv), first, n, cb.ctypes.data, fb.ctypes.data, sums.ctypes.data)
+        conflict = np.unpackbits(cb.view(np.uint8), bitorder="little")[:n].astype(bool)
+        full = np.unpackbits(fb.view(np.uint8), bitorder="little")[:n].astype(bool)
+        return conflict, full, [int(x) for x in sums]
 
     # ---- reference-only entry points
     def solve_assumps(self, assumps: Sequence[int], max_nof_restarts: int = 0):

@@ -242,6 +242,26 @@ void orc_batch_mt(void* hv, int mode, uint32_t seed, const int32_t* set_vars, in
     }
 }
 
+// Batch form of the solve-mode enumeration (mpi_base.cpp:148-169 order), BCP only.
+void orc_batch_enum(void* hv, const int32_t* vars_sorted, int k, uint64_t first, uint64_t n, uint64_t* conflict_bits,
+                    uint64_t* full_bits, uint64_t* sums) {
+    std::vector<int32_t> a((size_t)k);
+    for (uint64_t s = 0; s < n; s++) {
+        const uint64_t lint = first + s;
+        for (int r = 0; r < k; r++) a[r] = 2 * (vars_sorted[r] - 1) + (((lint >> r) & 1) ? 0 : 1);
+        orc_result r;
+        orc_bcp(hv, a.data(), k, &r, nullptr);
+        if (conflict_bits && r.conflict) conflict_bits[s >> 6] |= 1ull << (s & 63);
+        if (full_bits && r.full) full_bits[s >> 6] |= 1ull << (s & 63);
+        if (sums) {
+            sums[0] += (uint64_t)r.conflict;
+            sums[1] += (uint64_t)r.full;
+            sums[4] += r.propagations;
+            sums[5] += r.watch_scans;
+        }
+    }
+}
+
 // mpi_solver.cpp:218-245: incremental solve under assumptions + classification
 // state: 0 Solved, 1 SolvedOnPreprocessing, 2 Interrupted
 int orc_solve_assumps(void* hv, const int32_t* assumps, int n, int max_nof_restarts, orc_result* r,

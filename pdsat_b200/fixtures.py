@@ -373,3 +373,20 @@ def a5_2_cnf(stream_len: int = 114) -> Tuple[int, List[Clause], List[str], List[
         ks.append(t.xor(parts))
     comments = ["input variables 81", "output variables %d" % stream_len]
     return t.n, t.clauses, comments, ks
+
+
+def a5_2_weakened_instance(n_known: int = 32, seed: int = 9, stream_len: int = 114):
+    """BASELINE config 4: A5/2 CNF + keystream of a secret state + R4 + n_known of the 64
+    R1|R2|R3 bits as fixed assumptions; the other 64 - n_known state variables form the
+    decomposition set.  Returns (n_vars, clauses, fixed MiniSat literals, set variables (1-based,
+    ascending), secret state bits)."""
+    nv, cl, _, ks = a5_2_cnf(stream_len)
+    rng = np.random.default_rng(seed)
+    secret = rng.integers(0, 2, 81)
+    stream = A52Model(secret).stream(stream_len)
+    fixed = [2 * (v - 1) + (0 if bit else 1) for v, bit in zip(ks, stream)]
+    fixed += [2 * v + (0 if secret[v] else 1) for v in range(64, 81)]
+    known = sorted(int(v) for v in rng.choice(np.arange(64), size=n_known, replace=False))
+    fixed += [2 * v + (0 if secret[v] else 1) for v in known]
+    dset = [v + 1 for v in range(64) if v not in known]
+    return nv, cl, fixed, dset, secret
