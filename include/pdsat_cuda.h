@@ -252,6 +252,49 @@ int pdsat_enumerate(pdsat_db* db, const int32_t* set_vars, int32_t k, int32_t n_
 /* change the blocks of a single-point ENUM_BLOCKS batch (n_blocks <= the number it was created with) */
 int pdsat_batch_set_blocks(pdsat_batch* b, uint64_t n_blocks, const uint64_t* block_prefix);
 
+/* ---- hand-off of what BCP leaves open to a host CDCL ---------------------------------------
+ * A sample (predict) or assignment (solve) without conflict and without a full assignment needs
+ * search: in the reference the rest of solve() after the level-0 propagation
+ * (src_common/minisat/core/Solver.cc:775-885, called at src_mpi/mpi_predicter.cpp:731 and
+ * src_mpi/mpi_solver.cpp:218-226).  The library runs its own CDCL (pdsat_b200/host/cdcl.hpp, not
+ * the reference's code) on host threads, one incremental solver per thread over the uploaded
+ * clauses + fixed assumptions.  Verdicts are properties of the formula (equal to the reference's);
+ * decisions / propagations / conflicts are this solver's own counts. */
+typedef struct {
+    int64_t max_conflicts; /* per problem, < 0: none                                          */
+    int64_t max_restarts;  /* per problem, <= 0: none (max_nof_restarts)                      */
+    double max_seconds;    /* per problem, < 0: none (max_solving_time)                       */
+    int32_t n_threads;     /* <= 0: all host cores                                            */
+} pdsat_cdcl_limits;
+typedef struct {
+    uint64_t n_problems;   /* handed to the host                                              */
+    uint64_t n_sat, n_unsat, n_unknown;
+    uint64_t decisions, propagations, conflicts;
+    double seconds;        /* wall clock of the hand-off                                      */
+    int32_t threads;
+} pdsat_cdcl_stats;
+enum { PDSAT_SAT = 0, PDSAT_UNSAT = 1, PDSAT_UNKNOWN = 2 };
+/* n problems of k assumption literals each (MiniSat codes, row-major).  status[i] in
+ * {PDSAT_SAT, PDSAT_UNSAT, PDSAT_UNKNOWN}; props[i] (optional) = propagations of problem i;
+ * the first max_models satisfying assignments go to models[j*n_vars + v] in {0,1} with
+ * model_problem[j] = i (both optional). */
+int pdsat_cdcl_solve_many(pdsat_db* db, int64_t n, int32_t k, const int32_t* assumps, const pdsat_cdcl_limits* lim,
+                          uint8_t* status, uint64_t* props, int32_t max_models, int64_t* model_problem, uint8_t* models,
+                          int64_t* n_models, pdsat_cdcl_stats* stats);
+/* One point of a propagated batch (created with PDSAT_OUT_FLAGS): every sample gets a verdict -
+ * BCP conflicts are PDSAT_UNSAT, BCP models PDSAT_SAT, the undecided ones are solved on the host
+ * under the sample's assumptions.  cost[s] (optional) = Solver::propagations-like cost of the
+ * sample: the BCP trail for samples BCP decides without conflict (what the reference counts),
+ * the host solver's propagation count + the level-0 trail for handed-off samples, 0 for BCP
+ * conflicts (order dependent in the reference).  max_models caps the models returned
+ * from the handed-off samples (BCP's own models come from pdsat_batch_models). */
+int pdsat_batch_handoff(pdsat_batch* b, int32_t point, const pdsat_cdcl_limits* lim, uint8_t* status, uint64_t* cost,
+                        int32_t max_models, uint64_t* model_sample, uint8_t* models, int64_t* n_models,
+                        pdsat_cdcl_stats* stats);
+/* the values of the set variables of samples first..first+n-1 as the device used them:
+ * values[(s-first)*k + j] in {0,1} */
+int pdsat_batch_sample_values(pdsat_batch* b, int32_t point, uint64_t first, uint64_t n, uint8_t* values);
+
 /* ---- one-call form (host buffers in, host buffers out; the e2e path) ---------------- */
 int pdsat_eval_batch(pdsat_db* db, int32_t n_points, const pdsat_point* points, pdsat_cost* costs);
 

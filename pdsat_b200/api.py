@@ -31,6 +31,7 @@ EXPORTS = [
     "pdsat_mt19937_bool_rand", "pdsat_batch_peer_export", "pdsat_batch_peer_connect",
     "pdsat_batch_peer_disconnect", "pdsat_batch_h2d_bytes", "pdsat_db_gates", "pdsat_batch_set_first_draw",
     "pdsat_enumerate", "pdsat_batch_set_blocks",
+    "pdsat_cdcl_solve_many", "pdsat_batch_handoff", "pdsat_batch_sample_values",
 ]
 
 
@@ -63,6 +64,24 @@ class CDbInfo(C.Structure):
 class CEnumStats(C.Structure):
     _fields_ = [("n_assignments", C.c_uint64), ("n_conflict", C.c_uint64), ("n_models", C.c_uint64),
                 ("n_undecided", C.c_uint64), ("n_propagated", C.c_uint64), ("n_batches", C.c_uint64)]
+
+
+class CCdclLimits(C.Structure):
+    _fields_ = [("max_conflicts", C.c_int64), ("max_restarts", C.c_int64), ("max_seconds", C.c_double),
+                ("n_threads", C.c_int32)]
+
+
+class CCdclStats(C.Structure):
+    _fields_ = [("n_problems", C.c_uint64), ("n_sat", C.c_uint64), ("n_unsat", C.c_uint64), ("n_unknown", C.c_uint64),
+                ("decisions", C.c_uint64), ("propagations", C.c_uint64), ("conflicts", C.c_uint64),
+                ("seconds", C.c_double), ("threads", C.c_int32)]
+
+
+SAT, UNSAT, UNKNOWN = 0, 1, 2
+
+
+def _limits(max_conflicts=-1, max_restarts=-1, max_seconds=-1.0, n_threads=0):
+    return CCdclLimits(max_conflicts, max_restarts, max_seconds, n_threads)
 
 
 class CGate(C.Structure):
@@ -119,6 +138,12 @@ def lib():
     L.pdsat_enumerate.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_uint64, C.c_int32, C.c_uint64,
                                   C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(CEnumStats)]
     L.pdsat_batch_set_blocks.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p]
+    L.pdsat_cdcl_solve_many.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.POINTER(CCdclLimits), C.c_void_p,
+                                        C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.POINTER(C.c_int64),
+                                        C.POINTER(CCdclStats)]
+    L.pdsat_batch_handoff.argtypes = [C.c_void_p, C.c_int32, C.POINTER(CCdclLimits), C.c_void_p, C.c_void_p, C.c_int32,
+                                      C.c_void_p, C.c_void_p, C.POINTER(C.c_int64), C.POINTER(CCdclStats)]
+    L.pdsat_batch_sample_values.argtypes = [C.c_void_p, C.c_int32, C.c_uint64, C.c_uint64, C.c_void_p]
     _lib = L
     return L
 
@@ -252,6 +277,26 @@ class ClauseDb:
         n = min(ns.value, max_survivors)
         return surv[:n].copy(), ism[:n].astype(bool), st
 
+    def cdcl_solve_many(self, assumps: np.ndarray, max_models: int = 0, **limits):
+        """Host CDCL on n problems of k assumption literals (rows of `assumps`, MiniSat codes):
+        (status[n], props[n], model_problem[m], models[m, n_vars], CCdclStats)."""
+        a = np.ascontiguousarray(assumps, dtype=np.int32)
+        if a.ndim == 1:
+            a = a.reshape(1, -1)
+        n, k = a.shape
+        status = np.zeros(n, dtype=np.uint8)
+        props = np.zeros(n, dtype=np.uint64)
+        mp = np.zeros(max(max_models, 1), dtype=np.int64)
+        models = np.zeros((max(max_models, 1), self.n_vars), dtype=np.uint8)
+        nm = C.c_int64(0)
+        st = CCdclStats()
+        lim = _limits(**limits)
+        _check(lib().pdsat_cdcl_solve_many(self.h, n, k, a.ctypes.data if a.size else None, C.byref(lim), status.ctypes.data,
+                                           props.ctypes.data, max_models, mp.ctypes.data, models.ctypes.data, C.byref(nm),
+                                           C.byref(st)))
+        m = min(nm.value, max_models)
+        return status, props, mp[:m], models[:m], st
+
     def eval_batch(self, points: Sequence[Point]) -> List[Cost]:
         """One call, host buffers in / out (pdsat_eval_batch): the e2e path."""
         arr, keep = _cpoints(points)
@@ -338,6 +383,30 @@ class Batch:
 
     def peer_disconnect(self) -> None:
         _check(lib().pdsat_batch_peer_disconnect(self.h))
+
+    def sample_values(self, point: int = 0, first: int = 0, n: Optional[int] = None) -> np.ndarray:
+        if n is None:
+            n = self.points[point].n_samples - first
+        v = np.zeros((n, len(self.points[point].set_vars)), dtype=np.uint8)
+        _check(lib().pdsat_batch_sample_values(self.h, point, first, n, v.ctypes.data))
+        return v
+
+    def handoff(self, point: int = 0, max_models: int = 0, want_cost: bool = False, **limits):
+        """Verdict of EVERY sample of the point: BCP's where it decides, the host CDCL's for the
+        rest.  Returns (status[n], cost[n] | None, model_sample[m], models[m, n_vars], CCdclStats)."""
+        n = self.points[point].n_samples
+        status = np.zeros(n, dtype=np.uint8)
+        cost = np.zeros(n, dtype=np.uint64) if want_cost else None
+        ms = np.zeros(max(max_models, 1), dtype=np.uint64)
+        models = np.zeros((max(max_models, 1), self.db.n_vars), dtype=np.uint8)
+        nm = C.c_int64(0)
+        st = CCdclStats()
+        lim = _limits(**limits)
+        _check(lib().pdsat_batch_handoff(self.h, point, C.byref(lim), status.ctypes.data,
+                                         cost.ctypes.data if want_cost else None, max_models, ms.ctypes.data,
+                                         models.ctypes.data, C.byref(nm), C.byref(st)))
+        m = min(nm.value, max_models)
+        return status, cost, ms[:m], models[:m], st
 
     def costs(self) -> List[Cost]:
         out = (CCost * len(self.points))()

@@ -12,7 +12,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libpdsat_b200.so")
 SOURCES = ["pdsat_cuda.cu"]
-HEADERS = ["kernels.cuh", "host_db.hpp", "mt_jump.hpp", os.path.join("..", "..", "include", "pdsat_cuda.h")]
+HEADERS = ["kernels.cuh", "host_db.hpp", "mt_jump.hpp", "handoff.hpp", os.path.join("..", "host", "cdcl.hpp"),
+           os.path.join("..", "..", "include", "pdsat_cuda.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

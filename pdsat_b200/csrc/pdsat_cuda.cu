@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "../../include/pdsat_cuda.h"
+#include "handoff.hpp"
 #include "host_db.hpp"
 #include "kernels.cuh"
 #include "mt_jump.hpp"
@@ -47,6 +48,7 @@ struct pdsat_db {
     int warps_per_cta = 0, warp_bytes = 0, qcap = 0, smem_bytes = 0, grid = 0;
     // set_fixed_assumptions renumbers the live variables: batches created before it are stale
     uint64_t generation = 0;
+    CdclPool cdcl;  // host solvers for the hand-off (lazy)
     int live_batches = 0;
     bool zombie = false;  // pdsat_destroy was called while batches were alive
     // mt19937 jump polynomials x^(624*2^t) mod phi resident on the device (lazy)
@@ -1359,6 +1361,129 @@ int pdsat_enumerate(pdsat_db* db, const int32_t* set_vars, int32_t k, int32_t n_
     cleanup();
     if (!stop) stats->n_conflict = stats->n_assignments - stats->n_models - stats->n_undecided;
     if (n_survivors) *n_survivors = ns;
+    return PDSAT_OK;
+}
+
+static pdsat_host::Cdcl::Limits cdcl_limits(const pdsat_cdcl_limits* lim, int* n_threads) {
+    pdsat_host::Cdcl::Limits L;
+    *n_threads = 0;
+    if (lim) {
+        L.max_conflicts = lim->max_conflicts;
+        L.max_restarts = lim->max_restarts;
+        L.max_seconds = lim->max_seconds;
+        *n_threads = lim->n_threads;
+    }
+    return L;
+}
+
+static void cdcl_stats_out(const SolveManyOut& o, uint64_t n, pdsat_cdcl_stats* st) {
+    if (!st) return;
+    st->n_problems = n;
+    st->n_sat = o.n_sat;
+    st->n_unsat = o.n_unsat;
+    st->n_unknown = o.n_unknown;
+    st->decisions = o.decisions;
+    st->propagations = o.propagations;
+    st->conflicts = o.conflicts;
+    st->seconds = o.seconds;
+    st->threads = o.threads;
+}
+
+int pdsat_cdcl_solve_many(pdsat_db* db, int64_t n, int32_t k, const int32_t* assumps, const pdsat_cdcl_limits* lim,
+                          uint8_t* status, uint64_t* props, int32_t max_models, int64_t* model_problem, uint8_t* models,
+                          int64_t* n_models, pdsat_cdcl_stats* stats) {
+    if (!db || n < 0 || k < 0 || (n > 0 && k > 0 && !assumps) || (n > 0 && !status))
+        return fail(PDSAT_ERR_ARG, "pdsat_cdcl_solve_many: bad argument");
+    const HostDb& h = db->host;
+    for (int64_t i = 0; i < n * (int64_t)k; i++)
+        if (assumps[i] < 0 || (assumps[i] >> 1) >= h.n_vars) return fail(PDSAT_ERR_ARG, "pdsat_cdcl_solve_many: literal out of range");
+    int nt = 0;
+    const pdsat_host::Cdcl::Limits L = cdcl_limits(lim, &nt);
+    SolveManyOut o;
+    if (n_models) *n_models = 0;
+    if (n > 0) solve_many(db->cdcl, h, db->generation, n, k, assumps, L, nt, status, props, max_models, model_problem, models, n_models, o);
+    cdcl_stats_out(o, (uint64_t)n, stats);
+    return PDSAT_OK;
+}
+
+int pdsat_batch_sample_values(pdsat_batch* b, int32_t point, uint64_t first, uint64_t n, uint8_t* values) {
+    if (!b || !values || point < 0 || point >= (int)b->pts.size()) return fail(PDSAT_ERR_ARG, "pdsat_batch_sample_values: bad argument");
+    if (!b->filled) return fail(PDSAT_ERR_ARG, "pdsat_batch_sample_values: batch not filled");
+    const HostPoint& hp = b->pts[point];
+    if (first + n > hp.n_samples) return fail(PDSAT_ERR_ARG, "pdsat_batch_sample_values: range");
+    if (n == 0) return PDSAT_OK;
+    CU(cudaSetDevice(b->db->device));
+    CU(cudaStreamSynchronize(b->db->stream));
+    const size_t k = hp.set_vars.size();
+    const uint64_t g0 = first / 64, g1 = (first + n - 1) / 64;
+    std::vector<uint64_t> w((size_t)(g1 - g0 + 1) * hp.kp);
+    CU(cudaMemcpy(w.data(), b->d_words + hp.word_off + g0 * hp.kp, sizeof(uint64_t) * w.size(), cudaMemcpyDeviceToHost));
+    for (uint64_t s = first; s < first + n; s++) {
+        const uint64_t* gw = &w[(size_t)(s / 64 - g0) * hp.kp];
+        const int bit = (int)(s & 63);
+        uint8_t* dst = values + (s - first) * k;
+        for (size_t j = 0; j < k; j++) dst[j] = (uint8_t)((gw[j] >> bit) & 1ull);
+    }
+    return PDSAT_OK;
+}
+
+int pdsat_batch_handoff(pdsat_batch* b, int32_t point, const pdsat_cdcl_limits* lim, uint8_t* status, uint64_t* cost,
+                        int32_t max_models, uint64_t* model_sample, uint8_t* models, int64_t* n_models,
+                        pdsat_cdcl_stats* stats) {
+    if (!b || !status || point < 0 || point >= (int)b->pts.size()) return fail(PDSAT_ERR_ARG, "pdsat_batch_handoff: bad argument");
+    if (!b->d_conflict || !b->propagated) return fail(PDSAT_ERR_ARG, "pdsat_batch_handoff: needs PDSAT_OUT_FLAGS and a propagated batch");
+    if (cost && !b->d_trail) return fail(PDSAT_ERR_ARG, "pdsat_batch_handoff: cost needs PDSAT_OUT_TRAIL");
+    pdsat_db* db = b->db;
+    const HostDb& h = db->host;
+    const HostPoint& hp = b->pts[point];
+    const uint64_t n = hp.n_samples;
+    std::vector<uint64_t> cw((size_t)hp.n_groups), fw((size_t)hp.n_groups);
+    int rc = pdsat_batch_flags(b, point, cw.data(), fw.data());
+    if (rc) return rc;
+    std::vector<uint32_t> trail;
+    if (cost) {
+        trail.resize((size_t)n);
+        if ((rc = pdsat_batch_trail(b, point, trail.data()))) return rc;
+    }
+    std::vector<uint64_t> open_idx;
+    for (uint64_t s = 0; s < n; s++) {
+        const bool cf = (cw[s >> 6] >> (s & 63)) & 1, fu = (fw[s >> 6] >> (s & 63)) & 1;
+        status[s] = cf ? PDSAT_UNSAT : (fu ? PDSAT_SAT : PDSAT_UNKNOWN);
+        if (cost) cost[s] = cf ? 0 : trail[s];
+        if (!cf && !fu) open_idx.push_back(s);
+    }
+    if (n_models) *n_models = 0;
+    SolveManyOut o;
+    const size_t k = hp.set_vars.size();
+    if (!open_idx.empty()) {
+        // the assumptions of the open samples, as the device used them (from the bit-sliced words)
+        CU(cudaSetDevice(db->device));
+        std::vector<uint64_t> w((size_t)hp.n_groups * hp.kp);
+        CU(cudaMemcpy(w.data(), b->d_words + hp.word_off, sizeof(uint64_t) * w.size(), cudaMemcpyDeviceToHost));
+        std::vector<int32_t> assumps(open_idx.size() * k);
+        for (size_t i = 0; i < open_idx.size(); i++) {
+            const uint64_t s = open_idx[i];
+            const uint64_t* gw = &w[(size_t)(s / 64) * hp.kp];
+            for (size_t j = 0; j < k; j++)
+                assumps[i * k + j] = 2 * (hp.set_vars[j] - 1) + (((gw[j] >> (s & 63)) & 1ull) ? 0 : 1);
+        }
+        std::vector<uint8_t> st(open_idx.size());
+        std::vector<uint64_t> pr(open_idx.size());
+        std::vector<int64_t> mp((size_t)(max_models > 0 ? max_models : 0));
+        int nt = 0;
+        const pdsat_host::Cdcl::Limits L = cdcl_limits(lim, &nt);
+        int64_t nm = 0;
+        solve_many(db->cdcl, h, db->generation, (int64_t)open_idx.size(), (int32_t)k, assumps.data(), L, nt, st.data(), pr.data(),
+                   max_models, mp.data(), models, &nm, o);
+        for (size_t i = 0; i < open_idx.size(); i++) {
+            status[open_idx[i]] = st[i];
+            if (cost) cost[open_idx[i]] = (uint64_t)h.n_base_assigned + pr[i];
+        }
+        const int64_t stored = nm < max_models ? nm : max_models;
+        for (int64_t j = 0; j < stored && model_sample; j++) model_sample[j] = open_idx[(size_t)mp[(size_t)j]];
+        if (n_models) *n_models = nm;
+    }
+    cdcl_stats_out(o, open_idx.size(), stats);
     return PDSAT_OK;
 }
 
