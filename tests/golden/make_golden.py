@@ -116,6 +116,24 @@ def odls_sample():
             f.write("\n")
 
 
+def latin_conseq_rows():
+    """Data fixture: the 11 assumption rows (26 positive literals each: first row of square A and
+    8 cells of its second and third rows) of the reference's pdsat_conseq sample input
+    VS_latin_conseq/in:2-12 - the problems latin_square::SolveOneProblem
+    (src_common/latin_squares.cpp:133-233) is fed."""
+    rows = []
+    for line in open("/root/reference/VS_latin_conseq/in"):
+        t = line.split()
+        if len(t) > 2 and t[0] == "c" and t[1].isdigit():
+            rows.append([int(x) for x in t[1:]])
+    assert len(rows) == 11 and all(len(r) == 26 for r in rows)
+    with open(os.path.join(HERE, "latin_conseq_rows.txt"), "w") as f:
+        f.write("# assumption rows of the reference's VS_latin_conseq/in:2-12 (positive literals, 1-based\n"
+                "# variables p*1000 + i*100 + j*10 + z + 1); written by tests/golden/make_golden.py\n")
+        for r in rows:
+            f.write(" ".join(map(str, r)) + "\n")
+
+
 def rc2_golden():
     """Solver::gen_valid_assumptions_rc2 (Solver.cc:1293-1435) run by the reference itself on
     the weakened-Bivium cubes of SURVEY.md 8c-2b: template + keystream + the first N state bits
@@ -149,4 +167,5 @@ def rc2_golden():
 
 if __name__ == "__main__":
     odls_sample()
+    latin_conseq_rows()
     rc2_golden()

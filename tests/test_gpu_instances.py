@@ -131,3 +131,62 @@ def test_a52_weakened_instance(oracle_mod, cuda_lib):
         m = models[[int(x) for x in smp].index(idx)]
         assert [int(x) for x in m[:81]] == [int(x) for x in secret]
     assert c.n == 1024 and c.n_conflict >= 1
+
+
+def _clauses_satisfied(cl, model):
+    m = np.asarray(model, dtype=np.int8)
+    for c in cl:
+        if not any((m[abs(l) - 1] == 1) == (l > 0) for l in c):
+            return False
+    return True
+
+
+def test_odls_solve_one_problem_semantics(odls, oracle_mod):
+    """latin_square::SolveOneProblem (src_common/latin_squares.cpp:133-233): positive-literal
+    assumptions on one persistent solver.  (1) the 11 rows of the reference's own sample input
+    (VS_latin_conseq/in:2-12, 26 literals each): the device's BCP equals the reference BCP, the
+    hand-off under a small conflict budget never contradicts it;  (2) a known pair with the last
+    rows of square B left open: BCP + host CDCL complete it to a valid ODLS pair;  (3) one wrong
+    cell: refuted."""
+    from pdsat_b200 import api, fixtures as fx
+    nv, db, P, pairs = odls
+    _, cl = fx.odls_pair_cnf(10)
+    rows = [[int(x) for x in l.split()] for l in open(os.path.join(ROOT, "tests", "golden", "latin_conseq_rows.txt"))
+            if l.strip() and not l.startswith("#")]
+    assert len(rows) == 11 and all(len(r) == 26 for r in rows)
+    pts = [api.Point(r, 1, api.MODE_EXPLICIT, explicit_values=np.ones((1, 26), dtype=np.uint8)) for r in rows]
+    b = api.Batch(db, pts, api.OUT_FLAGS | api.OUT_TRAIL | api.OUT_ASSIGN)
+    b.run()
+    for p, r in enumerate(rows):
+        res, a = P.bcp([2 * (v - 1) for v in r])
+        conflict, full = b.flags(p)
+        assert bool(conflict[0]) == bool(res.conflict) and not full[0]
+        if not res.conflict:
+            assert int(b.trail(p)[0]) == res.trail_size and (b.assign(p)[0] == a).all()
+        status, _, ms, models, st = b.handoff(p, max_models=1, max_conflicts=300, n_threads=1)
+        if res.conflict:
+            assert status[0] == api.UNSAT and st.n_problems == 0
+        else:
+            assert st.n_problems == 1 and status[0] in (api.SAT, api.UNSAT, api.UNKNOWN)
+            if status[0] == api.SAT:
+                assert _clauses_satisfied(cl, models[0]) and all(models[0][v - 1] == 1 for v in r)
+    b.close()
+    # (2) + (3): square A and the first 7 rows of B of a known pair
+    a_sq, b_sq = pairs[0]
+    allv = fx.odls_assumptions_from_squares(10, a_sq, b_sq)
+    part = allv[:100] + allv[100:170]
+    bad = list(part)
+    bad[150] = bad[150] + 1 if (bad[150] - 1) % 10 != 9 else bad[150] - 1
+    pts = [api.Point(vs, 1, api.MODE_EXPLICIT, explicit_values=np.ones((1, len(vs)), dtype=np.uint8)) for vs in (part, bad)]
+    b = api.Batch(db, pts, api.OUT_FLAGS | api.OUT_TRAIL, max_models=4)
+    b.run()
+    status, _, ms, models, st = b.handoff(0, max_models=1, max_conflicts=200000, n_threads=1)
+    assert status[0] == api.SAT
+    if st.n_problems:  # completed by search: a valid pair that extends the assumptions
+        assert _clauses_satisfied(cl, models[0]) and all(models[0][v - 1] == 1 for v in part)
+    else:              # BCP alone completed it
+        found, _, _, bm = b.models()
+        assert found >= 1 and _clauses_satisfied(cl, bm[0])
+    status, *_ = b.handoff(1, max_conflicts=200000, n_threads=1)
+    assert status[0] == api.UNSAT
+    b.close()
