@@ -285,8 +285,9 @@ int pdsat_cdcl_solve_many(pdsat_db* db, int64_t n, int32_t k, const int32_t* ass
  * BCP conflicts are PDSAT_UNSAT, BCP models PDSAT_SAT, the undecided ones are solved on the host
  * under the sample's assumptions.  cost[s] (optional) = Solver::propagations-like cost of the
  * sample: the BCP trail for samples BCP decides without conflict (what the reference counts),
- * the host solver's propagation count + the level-0 trail for handed-off samples, 0 for BCP
- * conflicts (order dependent in the reference).  max_models caps the models returned
+ * the host solver's propagation count + the level-0 trail for handed-off samples; for a BCP
+ * conflict the level-0 trail + the k assumptions (the reference's count at a conflict depends
+ * on its watch order - this is the order-independent part of it).  max_models caps the models returned
  * from the handed-off samples (BCP's own models come from pdsat_batch_models). */
 int pdsat_batch_handoff(pdsat_batch* b, int32_t point, const pdsat_cdcl_limits* lim, uint8_t* status, uint64_t* cost,
                         int32_t max_models, uint64_t* model_sample, uint8_t* models, int64_t* n_models,

@@ -41,7 +41,7 @@ def needs_build() -> bool:
 
 HOST_DIR = os.path.join(HERE, "host")
 HOST_BIN = os.path.join(HERE, "pd-sat-b200")
-HOST_SOURCES = ["pd_sat_main.cpp", "dimacs.hpp", "predict.hpp"]
+HOST_SOURCES = ["pd_sat_main.cpp", "dimacs.hpp", "predict.hpp", "search.hpp"]
 
 
 def build_host(force: bool = False, verbose: bool = False) -> str:

@@ -1449,7 +1449,7 @@ int pdsat_batch_handoff(pdsat_batch* b, int32_t point, const pdsat_cdcl_limits* 
     for (uint64_t s = 0; s < n; s++) {
         const bool cf = (cw[s >> 6] >> (s & 63)) & 1, fu = (fw[s >> 6] >> (s & 63)) & 1;
         status[s] = cf ? PDSAT_UNSAT : (fu ? PDSAT_SAT : PDSAT_UNKNOWN);
-        if (cost) cost[s] = cf ? 0 : trail[s];
+        if (cost) cost[s] = cf ? (uint64_t)h.n_base_assigned + hp.set_vars.size() : trail[s];
         if (!cf && !fu) open_idx.push_back(s);
     }
     if (n_models) *n_models = 0;

@@ -71,8 +71,14 @@ struct Estimate {
     uint64_t solved = 0;       // solved on preprocessing (conflict or model)
 };
 
-// GetPredict (mpi_predicter.cpp:1976-1996) for evaluation_type "propagation" and
-// getCurPredictTime (:1846-1901) for "prep", on the device's integer accumulators.
+// GetPredict (mpi_predicter.cpp:1976-1996) on the device's integer accumulators:
+//   "prep"        getCurPredictTime (:1846-1901) with solved = samples BCP decides (conflict or
+//                 model) - exactly the reference's prep estimate;
+//   "bcp_trail"   mean BCP trail of the conflict-free samples (the size of the propagated
+//                 assignment; conflict samples count 0) x 2^k / proc - a BCP-only cost, NOT the
+//                 reference's "propagation" (which counts the propagations of the full CDCL run);
+//   "propagation" is computed by the caller from per-sample costs after the CDCL hand-off
+//                 (pd_sat_main.cpp Evaluator); this function then only supplies the counts.
 inline Estimate estimate(const pdsat_cost& c, size_t k, const std::string& eval, int proc_count) {
     Estimate e;
     e.solved = c.n_conflict + c.n_full;

@@ -88,14 +88,18 @@ class PointResult:
     solved: int                     # samples decided by BCP (conflict or model)
 
 
-def predict_from_cost(cost: api.Cost, k: int, evaluation_type: str = "propagation", proc_count: int = 1):
+def predict_from_cost(cost: api.Cost, k: int, evaluation_type: str = "prep", proc_count: int = 1):
     """The estimator arithmetic on the integer accumulators.
 
-    "propagation": cost_j = Solver::propagations of sample j.  Every partial sum of the
-    reference's sequential double accumulation is an integer < 2^53, hence exact, so
-    sum == float(integer sum) bit for bit; conflict samples contribute their (order-dependent)
-    count in the reference and are therefore reported separately here.
-    "prep": getCurPredictTime with solved = #samples solved on preprocessing."""
+    "prep": getCurPredictTime with solved = #samples solved on preprocessing (exactly the
+    reference's prep estimate).
+    "bcp_trail": cost_j = BCP trail of sample j (= Solver::propagations of a sample BCP decides
+    without conflict; 0 for conflict samples).  Every partial sum of a sequential double
+    accumulation of integers < 2^53 is exact, so sum == float(integer sum) bit for bit.  This is
+    a BCP-only cost, NOT the reference's "propagation" (CDCL propagations of the whole solve())."""
+    if evaluation_type not in ("prep", "bcp_trail"):
+        raise ValueError("evaluation_type must be 'prep' or 'bcp_trail' (the CDCL-based 'propagation' cost lives in the "
+                         "C++ host driver, pdsat_b200/host/pd_sat_main.cpp)")
     n = cost.n
     if evaluation_type == "prep":
         solved = cost.n_conflict + cost.n_full
@@ -126,8 +130,9 @@ def sample_variance(cost: api.Cost) -> float:
 class Predicter:
     """Scores decomposition sets on one GPU (or one rank of a multi-GPU job)."""
 
-    def __init__(self, db: api.ClauseDb, cnf_in_set_count: int = 1000, evaluation_type: str = "propagation",
-                 proc_count: int = 1, base_seed: int = 1, rank: int = 0, world: int = 1, all_reduce=None):
+    def __init__(self, db: api.ClauseDb, cnf_in_set_count: int = 1000, evaluation_type: str = "prep",
+                 proc_count: int = 1, base_seed: int = 1, rank: int = 0, world: int = 1, all_reduce=None,
+                 exhaustive_small_sets: bool = False):
         self.db = db
         self.cnf_in_set_count = cnf_in_set_count
         self.evaluation_type = evaluation_type
@@ -135,13 +140,17 @@ class Predicter:
         self.base_seed = base_seed
         self.rank, self.world = rank, world
         self.all_reduce = all_reduce  # callable(np.ndarray[int64]) -> summed array, or None
+        # the reference always DRAWS its samples; enumerating all 2^k assignments of a small set
+        # instead is an option, not the default
+        self.exhaustive_small_sets = exhaustive_small_sets
 
     def points_for(self, sets: Sequence[Sequence[int]]) -> List[api.Point]:
         pts = []
         for p, sv in enumerate(sets):
             n = samples_for_set(len(sv), self.cnf_in_set_count)
             lo, hi = shard_range(n, self.rank, self.world)
-            mode = api.MODE_ENUM if n == (1 << len(sv)) and len(sv) <= MAX_STEP_CNF_IN_SET else api.MODE_MT19937
+            mode = api.MODE_ENUM if (self.exhaustive_small_sets and n == (1 << len(sv)) and
+                                     len(sv) <= MAX_STEP_CNF_IN_SET) else api.MODE_MT19937
             pts.append(api.Point(list(sv), max(hi - lo, 0), mode, seed=self.base_seed + p, first_sample=lo))
         return pts
 

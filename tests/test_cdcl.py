@@ -150,7 +150,8 @@ def _handoff_vs_reference(orc, nv, cls, offs, lits, fixed, sv, vals, secret_rows
         srow = int(ms[j])
         for jj, v in enumerate(sv):
             assert models[j][v - 1] == vals[srow][jj]
-    assert (cost[conflict] == 0).all()
+    info = db.info()
+    assert (cost[conflict] == info.n_base_assigned + len(sv)).all()
     b.close()
     db.close()
     return n_open, status, st

@@ -79,7 +79,7 @@ def test_two_rank_sharding_and_allreduce(oracle_mod):
                 costs.append(float(r.trail_size))
         assert reduced[p][:5] == acc
         c = api.Cost(*reduced[p][:6])
-        s_, med, pred = pr.predict_from_cost(c, len(sv), "propagation", proc_count=4)
+        s_, med, pred = pr.predict_from_cost(c, len(sv), "bcp_trail", proc_count=4)
         if costs and acc[1] == 0:
             es, emed, epred = oracle_mod.predict_mean(np.asarray(costs), len(sv), 4)
             assert s_ == es

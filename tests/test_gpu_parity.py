@@ -420,7 +420,7 @@ def test_config0_predict_estimate_matches_reference_path(k, bivium, golden, orac
     ref_sum, ref_med, ref_pred = oracle_mod.predict_mean(cost, k, proc_count=4)
     db = api.ClauseDb(nv, offs, lits, device=0)
     db.set_fixed_assumptions(stream)
-    res = pr.Predicter(db, cnf_in_set_count=n, evaluation_type="propagation", proc_count=4, base_seed=1).evaluate([sv])[0]
+    res = pr.Predicter(db, cnf_in_set_count=n, evaluation_type="bcp_trail", proc_count=4, base_seed=1).evaluate([sv])[0]
     assert res.sum_cost == ref_sum
     assert abs(float((res.predict - np.longdouble(ref_pred)) / np.longdouble(ref_pred))) <= 1e-12
     assert abs(pr.sample_variance(res.cost) - (oracle_mod.sample_variance(cost) if cost.std() > 0 else 0.0)) <= \

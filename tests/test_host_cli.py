@@ -50,13 +50,26 @@ def test_cli_parse_only(cli, tmp_path):
     assert [int(x) for x in out] == [777, 13000, 67400, 177, 200, 0, 0]
 
 
+def _predict_rows(path):
+    """rows of a `predict` file (format of src_mpi/mpi_predicter.cpp:2147-2267) as dicts"""
+    rows = []
+    for line in open(path).read().splitlines():
+        t = line.split()
+        if len(t) > 10 and t[2] == "sum" and t[4] == "pred":
+            d = {"size": int(t[0]), "status": int(t[1]), "sum": float(t[3]), "pred": float(t[5])}
+            for key in ("min", "max", "med", "s^2", "stopped", "skipped", "solved", "prepr:"):
+                d[key] = float(t[t.index(key) + 1])
+            rows.append(d)
+    return rows
+
+
 @pytest.mark.gpu
 def test_cli_predict_matches_python_mirror(cli, tmp_path):
     import bench
     from pdsat_b200 import api, predicter as pr
     path, _ = _instance_file(tmp_path)
     n = 20000
-    for k, ev in ((30, "propagation"), (86, "propagation"), (87, "prep")):
+    for k, ev in ((30, "bcp_trail"), (86, "bcp_trail"), (87, "prep")):
         out = subprocess.check_output([cli, path, str(k), "-cnf_in_set=%d" % n, "-schema=bivium_Ending2", "-eval=" + ev],
                                       cwd=str(tmp_path)).decode()
         vals = dict(l.split(" ", 1) for l in out.strip().splitlines())
@@ -66,9 +79,32 @@ def test_cli_predict_matches_python_mirror(cli, tmp_path):
         res = pr.Predicter(db, cnf_in_set_count=n, evaluation_type=ev).evaluate([pr.schema_vars("bivium_Ending2", k)])[0]
         got = np.longdouble(vals["best_predict"])
         assert abs(float((got - res.predict) / res.predict)) <= 1e-12, (k, ev, vals, res.predict)
-        row = open(tmp_path / "predict").read().splitlines()[1].split()
-        assert int(row[0]) == k and int(row[8]) == n
-        assert int(row[6]) == res.cost.n_conflict and int(row[7]) == res.cost.n_full
+        text = open(tmp_path / "predict").read()
+        assert text.startswith("Processor count 1\nCount of CNF in set %d\n" % n) and "Best var num %d" % k in text
+        row = _predict_rows(tmp_path / "predict")[0]
+        assert row["size"] == k and row["solved"] == n and row["status"] == 2
+        assert row["prepr:"] == res.cost.n_conflict + res.cost.n_full
+        assert abs(row["pred"] - float(res.predict)) <= 0.006 * float(res.predict)  # %.2e column
+        g = open(tmp_path / "graph_file").read().splitlines()
+        assert g[0].startswith("# best_var_num best_predict_time") and g[1].split()[1] == str(k)
+
+
+@pytest.mark.gpu
+def test_cli_eval_modes(cli, tmp_path):
+    """-eval=time / watch_scans are refused; -eval=propagation hands the undecided samples to the
+    host CDCL under a conflict budget and marks the set STOPPED when samples are interrupted."""
+    path, _ = _instance_file(tmp_path)
+    for ev in ("time", "watch_scans"):
+        r = subprocess.run([cli, path, "30", "-cnf_in_set=100", "-schema=bivium_Ending2", "-eval=" + ev], cwd=str(tmp_path),
+                           capture_output=True)
+        assert r.returncode != 0 and b"not supported" in r.stderr
+    path2, _ = _instance_file(tmp_path, fixed_state_bits=110)
+    out = subprocess.check_output([cli, path2, "20", "-cnf_in_set=256", "-schema=bivium_Ending2", "-eval=propagation",
+                                   "-max_conflicts=100000", "-threads=2"], cwd=str(tmp_path)).decode()
+    vals = dict(l.split(" ", 1) for l in out.strip().splitlines())
+    assert float(vals["best_predict"]) > 0
+    row = _predict_rows(tmp_path / "predict")[0]
+    assert row["status"] == 2 and row["stopped"] == 0 and row["solved"] == 256
 
 
 @pytest.mark.gpu
@@ -76,10 +112,12 @@ def test_cli_deep_predict_step(cli, tmp_path):
     """One tabu step: the centre + its 177 Hamming-1 neighbours in one batch."""
     path, _ = _instance_file(tmp_path)
     out = subprocess.check_output([cli, path, "86", "-cnf_in_set=2000", "-schema=bivium_Ending2", "-eval=prep",
-                                   "-deep_predict=1", "-max_steps=1"], cwd=str(tmp_path)).decode()
-    vals = dict(l.split(" ", 1) for l in out.strip().splitlines())
+                                   "-deep_predict=6", "-max_steps=1"], cwd=str(tmp_path)).decode()
+    vals = dict(l.split(" ", 1) for l in out.strip().splitlines() if not l.startswith("centre"))
     assert int(vals["points_evaluated"]) == 178
     assert float(vals["best_predict"]) < 1e308
+    assert len(_predict_rows(tmp_path / "predict")) == 177
+    assert "L2 point # : set_count : size" in open(tmp_path / "L2_list").read()
 
 
 @pytest.mark.gpu
