@@ -140,3 +140,35 @@ def test_cli_solve_weakened_bivium_kat(cli, tmp_path):
     assert sat_idx == [expect]
     model = open(tmp_path / "satisfying_assignments").read().split()[0]
     assert [int(c) for c in model[:177]] == [int(b) for b in secret]
+
+
+@pytest.mark.gpu
+def test_cli_interval_estimation(cli, tmp_path, oracle_mod):
+    """-interval_predict (calculateIntervalEstimation, src_mpi/mpi_predicter.cpp:3058-3181, rc2):
+    `size` consecutive assignments in the binary order of Solver::gen_valid_assumptions_rc2
+    (d_set[0] most significant, Solver.cc:1380-1423) from a random corner; the number solved on
+    preprocessing / surviving BCP equals the reference BCP's count over the same interval."""
+    import bench
+    path, secret = _instance_file(tmp_path, fixed_state_bits=140)
+    k, size, seed = 30, 1 << 15, 5
+    out = subprocess.check_output([cli, path, str(k), "-schema=bivium_Ending2", "-interval_predict", "-interval_size=%d" % size,
+                                   "-interval_required=50", "-seed=%d" % seed, "-max_conflicts=50000"], cwd=str(tmp_path)).decode()
+    vals = dict(l.split(" ", 1) for l in out.strip().splitlines())
+    sv = sorted(177 - i for i in range(k))
+    bits = oracle_mod.bool_rand(seed, 0, k)
+    start = 0
+    for b in bits:
+        start = (start << 1) | int(b)
+    start = min(start, (1 << k) - size)
+    assert int(vals["interval_start"]) == start and int(vals["interval_size"]) == size
+    nv, cl, offs, lits, stream = bench.instance()
+    O = oracle_mod.Oracle(nv, offs, lits, "port")
+    O.add_units(list(stream) + [2 * v + (0 if secret[v] else 1) for v in range(140)])
+    conflict, full, sums = O.batch_enum(sv[::-1], start, size)   # bit 0 of the index = last variable
+    n_surv = int((~conflict & ~full).sum())
+    assert int(vals["interval_nonprepr_number"]) == n_surv
+    assert int(vals["interval_prepr_number"]) == size - n_surv
+    solved = vals["survivors_solved"].split()
+    assert int(solved[0]) == min(50, n_surv)
+    assert int(solved[0]) == int(solved[2]) + int(solved[4]) + int(solved[6])
+    assert float(vals["interval_predict"]) > 0
