@@ -429,6 +429,11 @@ struct HostDb {
             occ.resize(occ_pairs.size());
             std::vector<uint32_t> pos(occ_off.begin(), occ_off.end() - 1);
             for (auto& pr : occ_pairs) occ[pos[pr.first]++] = pr.second;
+            // every list: short clauses first, so that the lanes of a trip agree on how many of the
+            // 8 record slots are in use (the device skips pad slot pairs)
+            for (size_t l = 0; l < (size_t)2 * n_live; l++)
+                std::stable_sort(occ.begin() + occ_off[l], occ.begin() + occ_off[l + 1],
+                                 [&](uint32_t x, uint32_t y) { return rec_len[x] < rec_len[y]; });
             occrec.resize(occ.size() * REC_SLOTS);
             for (size_t i = 0; i < occ.size(); i++) inline_record(occ[i], &occrec[i * REC_SLOTS]);
             // gates: records + per-variable lists

@@ -561,7 +561,7 @@ __device__ __forceinline__ void imply_slot(const WarpCtx& c, uint32_t m, uint64_
 }
 
 __device__ __forceinline__ void eval_clause(const uint4& r0, const uint4* __restrict__ rec, const WarpCtx& c,
-                                            uint64_t live) {
+                                            uint64_t live, uint32_t pad2) {
     uint64_t ge1 = 0, ge2 = 0, sat = 0;
     const bool indirect = rec_slot(r0, 7) == REC_INDIRECT_D;
     if (indirect) {
@@ -577,8 +577,21 @@ __device__ __forceinline__ void eval_clause(const uint4& r0, const uint4* __rest
             cur++;
         } while (more);
     } else {
-#pragma unroll
-        for (int j = 0; j < 8; j++) accumulate_slot(c.S, rec_slot(r0, j), ge1, ge2, sat);
+        // literals fill the slots from the front; a word of two pad slots ends the clause
+        accumulate_slot(c.S, r0.x & 0xFFFFu, ge1, ge2, sat);
+        accumulate_slot(c.S, r0.x >> 16, ge1, ge2, sat);
+        if (r0.y != pad2) {
+            accumulate_slot(c.S, r0.y & 0xFFFFu, ge1, ge2, sat);
+            accumulate_slot(c.S, r0.y >> 16, ge1, ge2, sat);
+            if (r0.z != pad2) {
+                accumulate_slot(c.S, r0.z & 0xFFFFu, ge1, ge2, sat);
+                accumulate_slot(c.S, r0.z >> 16, ge1, ge2, sat);
+                if (r0.w != pad2) {
+                    accumulate_slot(c.S, r0.w & 0xFFFFu, ge1, ge2, sat);
+                    accumulate_slot(c.S, r0.w >> 16, ge1, ge2, sat);
+                }
+            }
+        }
     }
     const uint64_t confl = ~ge1 & live;
     const uint64_t unit = ge1 & ~ge2 & ~sat & live;
@@ -597,8 +610,20 @@ __device__ __forceinline__ void eval_clause(const uint4& r0, const uint4* __rest
                 cur++;
             } while (more);
         } else {
-#pragma unroll
-            for (int j = 0; j < 8; j++) imply_slot(c, rec_slot(r0, j), unit);
+            imply_slot(c, r0.x & 0xFFFFu, unit);
+            imply_slot(c, r0.x >> 16, unit);
+            if (r0.y != pad2) {
+                imply_slot(c, r0.y & 0xFFFFu, unit);
+                imply_slot(c, r0.y >> 16, unit);
+                if (r0.z != pad2) {
+                    imply_slot(c, r0.z & 0xFFFFu, unit);
+                    imply_slot(c, r0.z >> 16, unit);
+                    if (r0.w != pad2) {
+                        imply_slot(c, r0.w & 0xFFFFu, unit);
+                        imply_slot(c, r0.w >> 16, unit);
+                    }
+                }
+            }
         }
     }
 }
@@ -674,10 +699,10 @@ __device__ __forceinline__ void eval_gate(const uint4& r, const WarpCtx& c, uint
 }
 
 __device__ __forceinline__ void eval_record(const uint4& r, const uint4* __restrict__ rec, const WarpCtx& c,
-                                            uint64_t live) {
+                                            uint64_t live, uint32_t pad2) {
     const uint32_t tag = r.w >> 16;
     if (tag >= REC_TAG_MIN_D && tag < REC_INDIRECT_D) eval_gate(r, c, live);
-    else eval_clause(r, rec, c, live);
+    else eval_clause(r, rec, c, live, pad2);
 }
 
 __device__ __forceinline__ uint64_t shfl64(uint64_t v, int src) {
@@ -848,6 +873,7 @@ bcp_kernel(DbDev db, BatchDev b, int warp_bytes) {
     }
     __syncwarp();
 
+    const uint32_t pad2 = (uint32_t)db.n_lit | ((uint32_t)db.n_lit << 16);  // two pad slots
     WarpAcc acc;
     acc.n = acc.n_conflict = acc.n_full = acc.sum = acc.sumsq = acc.n_impl = acc.pops = acc.touched = 0;
     acc.point = -1;
@@ -1003,7 +1029,7 @@ bcp_kernel(DbDev db, BatchDev b, int warp_bytes) {
                 for (uint32_t i = lane; i < P_cand_cnt; i += 32) {
                     const uint4 cur = r;
                     if (i + 32 < P_cand_cnt) r = __ldg(&list[i + 32]);
-                    eval_record(cur, db.rec, c, live);
+                    eval_record(cur, db.rec, c, live, pad2);
                 }
             }
 
@@ -1086,7 +1112,7 @@ bcp_kernel(DbDev db, BatchDev b, int warp_bytes) {
                             const uint32_t bq = __shfl_sync(0xffffffffu, cbase, q & 31);
                             if (i < total) {
                                 const uint4 r = __ldg(&db.occrec[bq + i]);
-                                eval_clause(r, db.rec, c, live);
+                                eval_clause(r, db.rec, c, live, pad2);
                             }
                         }
                     }
