@@ -462,32 +462,55 @@ __device__ __forceinline__ void mbar_wait_s(uint32_t bar, uint32_t parity) {
 
 // ------------------------------------------------------------------ BCP
 // Per-warp working set in shared memory (one warp owns one group of 64 samples):
-//   S[l]      64-bit plane per literal: samples in which literal l is TRUE.  S[2v], S[2v+1] (the
-//             TRUE and FALSE plane of variable v) are adjacent: one 16-byte load fetches both
+//   S[l]      one plane per literal: samples in which literal l is TRUE.  S[2v], S[2v+1] (the
+//             TRUE and FALSE plane of variable v) are adjacent: one vector load fetches both
 //   fill      bitset: literals that gained samples since they were last visited - the frontier
 //             under construction (making a literal true = atomicOr on its plane + one atomicOr here)
 //   drain     bitset: the frontier being visited (the two swap roles at every level: the
 //             propagation is level-synchronous, breadth first)
 //   tset      bitset: literals implied in this group (undo list, per-sample trail counts)
 //   ring      multi-stage ring of assumption-word tiles filled by bulk async copies
+// The plane type PT is a template parameter: uint64_t = the 64 samples of a group in one pass;
+// uint32_t = two passes of 32 samples each over half-size planes.  Half-size planes halve the
+// shared memory per warp (twice the warps per SM for large instances: ODLS 5 -> 11, A5/2 1 -> 3)
+// and make every bit operation a native 32-bit one; the price is that a literal implied in both
+// halves is visited twice.  The host picks per database (pdsat_cuda.cu launch_shape).
+template <typename PT>
 struct WarpCtx {
-    uint64_t* S;
+    PT* S;
     uint32_t* fill;
     uint32_t* drain;
     uint32_t* tset;
-    uint64_t* dead;  // samples in conflict
+    PT* dead;  // samples in conflict
 };
 
-// 64-bit OR into shared memory as two native 32-bit ATOMS.OR (a 64-bit shared atomicOr
-// compiles to a compare-and-swap spin loop); returns the previous value of the halves touched
-__device__ __forceinline__ uint64_t or64_shared(uint64_t* p, uint64_t v) {
-    uint32_t* q = reinterpret_cast<uint32_t*>(p);
-    const uint32_t lo = (uint32_t)v, hi = (uint32_t)(v >> 32);
-    uint32_t olo = 0, ohi = 0;
-    if (lo) olo = atomicOr(q, lo);
-    if (hi) ohi = atomicOr(q + 1, hi);
-    return ((uint64_t)ohi << 32) | olo;
-}
+template <typename PT>
+struct Plane;
+template <>
+struct Plane<uint64_t> {
+    typedef ulonglong2 Pair;
+    static constexpr int W = 64;
+    static __device__ __forceinline__ int popc(uint64_t v) { return __popcll(v); }
+    static __device__ __forceinline__ int ffs(uint64_t v) { return __ffsll((long long)v); }
+    // OR into shared memory as two native 32-bit ATOMS.OR (a 64-bit shared atomicOr compiles to
+    // a compare-and-swap spin loop); returns the previous value of the halves touched
+    static __device__ __forceinline__ uint64_t or_shared(uint64_t* p, uint64_t v) {
+        uint32_t* q = reinterpret_cast<uint32_t*>(p);
+        const uint32_t lo = (uint32_t)v, hi = (uint32_t)(v >> 32);
+        uint32_t olo = 0, ohi = 0;
+        if (lo) olo = atomicOr(q, lo);
+        if (hi) ohi = atomicOr(q + 1, hi);
+        return ((uint64_t)ohi << 32) | olo;
+    }
+};
+template <>
+struct Plane<uint32_t> {
+    typedef uint2 Pair;
+    static constexpr int W = 32;
+    static __device__ __forceinline__ int popc(uint32_t v) { return __popc(v); }
+    static __device__ __forceinline__ int ffs(uint32_t v) { return __ffs((int)v); }
+    static __device__ __forceinline__ uint32_t or_shared(uint32_t* p, uint32_t v) { return atomicOr(p, v); }
+};
 
 // make literal l true in the samples `bits` (Solver.cc:579-585 uncheckedEnqueue, for up to 64
 // samples at once).  Planes only gain bits; a literal that gained a bit joins the next frontier,
@@ -498,15 +521,16 @@ __device__ __forceinline__ uint64_t or64_shared(uint64_t* p, uint64_t v) {
 // plane (shared-memory operations of a warp complete in order), so no such sample is missed.
 // Clauses would notice the contradiction by themselves (all their literals are false); two gates
 // that read the variable through opposite polarities would each see a value that suits them.
-__device__ __forceinline__ void set_true(const WarpCtx& c, uint32_t l, uint64_t bits) {
-    const uint64_t old = or64_shared(&c.S[l], bits);
-    const uint64_t contra = bits & *(const volatile uint64_t*)&c.S[l ^ 1u];
-    if (contra) or64_shared(c.dead, contra);
+template <typename PT>
+__device__ __forceinline__ void set_true(const WarpCtx<PT>& c, uint32_t l, PT bits) {
+    const PT old = Plane<PT>::or_shared(&c.S[l], bits);
+    const PT contra = bits & *(const volatile PT*)&c.S[l ^ 1u];
+    if (contra) Plane<PT>::or_shared(c.dead, contra);
     if (bits & ~old) atomicOr(&c.fill[l >> 5], 1u << (l & 31));
 }
 
 // variable with TRUE-plane code tcode (even): true in the samples t, false in the samples f
-__device__ __forceinline__ void set_pair(const WarpCtx& c, uint32_t tcode, uint64_t t, uint64_t f) {
+__device__ __forceinline__ void set_pair(const WarpCtx<uint64_t>& c, uint32_t tcode, uint64_t t, uint64_t f) {
     uint32_t* q = reinterpret_cast<uint32_t*>(c.S + tcode);  // T.lo T.hi F.lo F.hi
     const uint32_t tl = (uint32_t)t, th = (uint32_t)(t >> 32), fl = (uint32_t)f, fh = (uint32_t)(f >> 32);
     uint32_t nt = 0, nf = 0;
@@ -516,9 +540,20 @@ __device__ __forceinline__ void set_pair(const WarpCtx& c, uint32_t tcode, uint6
     if (fh) nf |= fh & ~atomicOr(q + 3, fh);
     const volatile uint64_t* now = c.S + tcode;
     const uint64_t contra = (t & now[1]) | (f & now[0]);
-    if (contra) or64_shared(c.dead, contra);
+    if (contra) Plane<uint64_t>::or_shared(c.dead, contra);
     const uint32_t m = (nt ? 1u : 0u) | (nf ? 2u : 0u);
     if (m) atomicOr(&c.fill[tcode >> 5], m << (tcode & 31));  // both literals sit in one word
+}
+__device__ __forceinline__ void set_pair(const WarpCtx<uint32_t>& c, uint32_t tcode, uint32_t t, uint32_t f) {
+    uint32_t* q = c.S + tcode;  // T F
+    uint32_t nt = 0, nf = 0;
+    if (t) nt = t & ~atomicOr(q, t);
+    if (f) nf = f & ~atomicOr(q + 1, f);
+    const volatile uint32_t* now = q;
+    const uint32_t contra = (t & now[1]) | (f & now[0]);
+    if (contra) atomicOr(c.dead, contra);
+    const uint32_t m = (nt ? 1u : 0u) | (nf ? 2u : 0u);
+    if (m) atomicOr(&c.fill[tcode >> 5], m << (tcode & 31));
 }
 
 __device__ __forceinline__ uint32_t rec_slot(const uint4& r, int j) {
@@ -526,9 +561,10 @@ __device__ __forceinline__ uint32_t rec_slot(const uint4& r, int j) {
     return (j & 1) ? (w >> 16) : (w & 0xFFFFu);
 }
 
-// (S[code & ~1], S[code | 1]) with one 16-byte shared load
-__device__ __forceinline__ void ld_pair(const uint64_t* S, uint32_t code, uint64_t& even, uint64_t& odd) {
-    const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(S + (code & ~1u));
+// (S[code & ~1], S[code | 1]) with one vector shared load
+template <typename PT>
+__device__ __forceinline__ void ld_pair(const PT* S, uint32_t code, PT& even, PT& odd) {
+    const typename Plane<PT>::Pair v = *reinterpret_cast<const typename Plane<PT>::Pair*>(S + (code & ~1u));
     even = v.x;
     odd = v.y;
 }
@@ -542,12 +578,12 @@ static constexpr uint32_t REC_GATE_XOR_D = 0xFFF0u, REC_GATE_ANDXOR_D = 0xFFF2u,
 // Clause slots hold the code m of the literal's FALSE plane; its TRUE plane is m ^ 1.
 //   ge1 / ge2 = samples with >= 1 / >= 2 non-false literals,  sat = samples with a true literal
 // Unused slots point at the pad plane pair (FALSE plane all ones, TRUE plane zero).
-__device__ __forceinline__ void accumulate_slot(const uint64_t* S, uint32_t m, uint64_t& ge1, uint64_t& ge2,
-                                                uint64_t& sat) {
-    uint64_t e, o;
+template <typename PT>
+__device__ __forceinline__ void accumulate_slot(const PT* S, uint32_t m, PT& ge1, PT& ge2, PT& sat) {
+    PT e, o;
     ld_pair(S, m, e, o);
-    const uint64_t f = (m & 1u) ? o : e, t = (m & 1u) ? e : o;
-    const uint64_t nf = ~f;
+    const PT f = (m & 1u) ? o : e, t = (m & 1u) ? e : o;
+    const PT nf = ~f;
     ge2 |= ge1 & nf;
     ge1 |= nf;
     sat |= t;
@@ -555,14 +591,16 @@ __device__ __forceinline__ void accumulate_slot(const uint64_t* S, uint32_t m, u
 
 // in the samples of `unit` the clause has exactly one non-false literal and it is undefined: make
 // it true (Solver.cc:641-648 uncheckedEnqueue(first, cr))
-__device__ __forceinline__ void imply_slot(const WarpCtx& c, uint32_t m, uint64_t unit) {
-    const uint64_t imp = unit & ~c.S[m];
+template <typename PT>
+__device__ __forceinline__ void imply_slot(const WarpCtx<PT>& c, uint32_t m, PT unit) {
+    const PT imp = unit & ~c.S[m];
     if (imp) set_true(c, m ^ 1u, imp);
 }
 
-__device__ __forceinline__ void eval_clause(const uint4& r0, const uint4* __restrict__ rec, const WarpCtx& c,
-                                            uint64_t live, uint32_t pad2) {
-    uint64_t ge1 = 0, ge2 = 0, sat = 0;
+template <typename PT>
+__device__ __forceinline__ void eval_clause(const uint4& r0, const uint4* __restrict__ rec, const WarpCtx<PT>& c, PT live,
+                                            uint32_t pad2) {
+    PT ge1 = 0, ge2 = 0, sat = 0;
     const bool indirect = rec_slot(r0, 7) == REC_INDIRECT_D;
     if (indirect) {
         uint32_t cur = r0.x;
@@ -593,9 +631,9 @@ __device__ __forceinline__ void eval_clause(const uint4& r0, const uint4* __rest
             }
         }
     }
-    const uint64_t confl = ~ge1 & live;
-    const uint64_t unit = ge1 & ~ge2 & ~sat & live;
-    if (confl) or64_shared(c.dead, confl);
+    const PT confl = ~ge1 & live;
+    const PT unit = ge1 & ~ge2 & ~sat & live;
+    if (confl) Plane<PT>::or_shared(c.dead, confl);
     if (unit) {
         if (indirect) {
             uint32_t cur = r0.x;
@@ -628,25 +666,27 @@ __device__ __forceinline__ void eval_clause(const uint4& r0, const uint4* __rest
     }
 }
 
-// Gate in closed form on 64 samples.  XOR: x_0 ^ ... ^ x_6 = p.  ANDXOR: x_0 ^ ... ^ x_4 ^ q = p
-// with q = Lb & Lc (q is known 1 where both literals are true, known 0 where one is false).
-// Members = the xor variables (and q).  Conflict where no member is unknown and the parity is
-// wrong; where exactly one member is unknown it takes the value  p ^ xor(known values).  For the
-// product: q must be 1 -> Lb and Lc become true; q must be 0 and one literal is true -> the
-// other becomes false.  Equal to unit propagation over the gate's clauses (tests/test_gates.py).
-// The two kinds share one instruction stream (selects on the kind mask), so a warp that mixes
-// them does not diverge until something is actually implied.
-__device__ __forceinline__ void imply_var(const WarpCtx& c, uint32_t tcode, uint64_t imp, uint64_t par) {
-    if (imp) set_pair(c, tcode, imp & par, imp & ~par);
+// Gate in closed form on the samples of a plane.  XOR: x_0 ^ ... ^ x_6 = p.  ANDXOR:
+// x_0 ^ ... ^ x_4 ^ q = p with q = Lb & Lc (q is known 1 where both literals are true, known 0
+// where one is false).  Members = the xor variables (and q).  Conflict where no member is unknown
+// and the parity is wrong; where exactly one member is unknown it takes the value
+// p ^ xor(known values).  For the product: q must be 1 -> Lb and Lc become true; q must be 0 and
+// one literal is true -> the other becomes false.  Equal to unit propagation over the gate's
+// clauses (tests/test_gates.py).  The two kinds share one instruction stream (selects on the kind
+// mask), so a warp that mixes them does not diverge until something is actually implied.
+template <typename PT>
+__device__ __forceinline__ void imply_var(const WarpCtx<PT>& c, uint32_t tcode, PT imp, PT par) {
+    if (imp) set_pair(c, tcode, (PT)(imp & par), (PT)(imp & ~par));
 }
 
-__device__ __forceinline__ void eval_gate(const uint4& r, const WarpCtx& c, uint64_t live) {
+template <typename PT>
+__device__ __forceinline__ void eval_gate(const uint4& r, const WarpCtx<PT>& c, PT live) {
     const uint32_t tag = r.w >> 16;
-    const uint64_t am = (tag & 2u) ? ~0ull : 0ull;  // ANDXOR
-    uint64_t par = (tag & 1u) ? ~0ull : 0ull;       // p ^ xor(values): must end up 0
-    uint64_t any = 0, two = 0;
-    uint64_t u0, u1, u2, u3, u4;
-    uint64_t t, f;
+    const PT am = (tag & 2u) ? ~(PT)0 : (PT)0;  // ANDXOR
+    PT par = (tag & 1u) ? ~(PT)0 : (PT)0;       // p ^ xor(values): must end up 0
+    PT any = 0, two = 0;
+    PT u0, u1, u2, u3, u4;
+    PT t, f;
 #define PDSAT_XVAR(U, CODE)              \
     ld_pair(c.S, (CODE), t, f);          \
     U = ~(t | f);                        \
@@ -661,36 +701,36 @@ __device__ __forceinline__ void eval_gate(const uint4& r, const WarpCtx& c, uint
 #undef PDSAT_XVAR
     // slots 5, 6: two more xor variables (TRUE-plane codes, even) or the literals Lb, Lc
     const uint32_t c5 = r.z >> 16, c6 = r.w & 0xFFFFu;
-    uint64_t e, o;
+    PT e, o;
     ld_pair(c.S, c5, e, o);
-    const uint64_t tb = (c5 & 1u) ? o : e, fb = (c5 & 1u) ? e : o;
+    const PT tb = (c5 & 1u) ? o : e, fb = (c5 & 1u) ? e : o;
     ld_pair(c.S, c6, e, o);
-    const uint64_t tc = (c6 & 1u) ? o : e, fc = (c6 & 1u) ? e : o;
-    const uint64_t q1 = tb & tc;
-    const uint64_t m5 = (~(tb | fb) & ~am) | (~(q1 | fb | fc) & am);  // x5 unknown / q unknown
-    const uint64_t m6 = ~(tc | fc) & ~am;                              // x6 unknown / -
+    const PT tc = (c6 & 1u) ? o : e, fc = (c6 & 1u) ? e : o;
+    const PT q1 = tb & tc;
+    const PT m5 = (~(tb | fb) & ~am) | (~(q1 | fb | fc) & am);  // x5 unknown / q unknown
+    const PT m6 = ~(tc | fc) & ~am;                              // x6 unknown / -
     par ^= ((tb ^ tc) & ~am) | (q1 & am);
     two |= any & m5;
     any |= m5;
     two |= any & m6;
     any |= m6;
-    const uint64_t confl = ~any & par & live;
-    const uint64_t one = any & ~two & live;
-    if (confl) or64_shared(c.dead, confl);
+    const PT confl = ~any & par & live;
+    const PT one = any & ~two & live;
+    if (confl) Plane<PT>::or_shared(c.dead, confl);
     if (one) {
-        imply_var(c, r.x & 0xFFFFu, one & u0, par);
-        imply_var(c, r.x >> 16, one & u1, par);
-        imply_var(c, r.y & 0xFFFFu, one & u2, par);
-        imply_var(c, r.y >> 16, one & u3, par);
-        imply_var(c, r.z & 0xFFFFu, one & u4, par);
-        const uint64_t i5 = one & m5, i6 = one & m6;
+        imply_var(c, r.x & 0xFFFFu, (PT)(one & u0), par);
+        imply_var(c, r.x >> 16, (PT)(one & u1), par);
+        imply_var(c, r.y & 0xFFFFu, (PT)(one & u2), par);
+        imply_var(c, r.y >> 16, (PT)(one & u3), par);
+        imply_var(c, r.z & 0xFFFFu, (PT)(one & u4), par);
+        const PT i5 = one & m5, i6 = one & m6;
         if (i5 | i6) {
             if (!am) {
                 imply_var(c, c5, i5, par);
                 imply_var(c, c6, i6, par);
             } else {
-                const uint64_t s1 = i5 & par, s0 = i5 & ~par;
-                const uint64_t b_true = s1 & ~tb, b_false = s0 & tc, c_true = s1 & ~tc, c_false = s0 & tb;
+                const PT s1 = i5 & par, s0 = i5 & ~par;
+                const PT b_true = s1 & ~tb, b_false = s0 & tc, c_true = s1 & ~tc, c_false = s0 & tb;
                 if (b_true | b_false) set_pair(c, c5 & ~1u, (c5 & 1u) ? b_false : b_true, (c5 & 1u) ? b_true : b_false);
                 if (c_true | c_false) set_pair(c, c6 & ~1u, (c6 & 1u) ? c_false : c_true, (c6 & 1u) ? c_true : c_false);
             }
@@ -698,8 +738,9 @@ __device__ __forceinline__ void eval_gate(const uint4& r, const WarpCtx& c, uint
     }
 }
 
-__device__ __forceinline__ void eval_record(const uint4& r, const uint4* __restrict__ rec, const WarpCtx& c,
-                                            uint64_t live, uint32_t pad2) {
+template <typename PT>
+__device__ __forceinline__ void eval_record(const uint4& r, const uint4* __restrict__ rec, const WarpCtx<PT>& c, PT live,
+                                            uint32_t pad2) {
     const uint32_t tag = r.w >> 16;
     if (tag >= REC_TAG_MIN_D && tag < REC_INDIRECT_D) eval_gate(r, c, live);
     else eval_clause(r, rec, c, live, pad2);
@@ -713,6 +754,10 @@ __device__ __forceinline__ uint64_t shfl_down64(uint64_t v, int d) {
     return ((uint64_t)__shfl_down_sync(0xffffffffu, (uint32_t)(v >> 32), d) << 32) |
            __shfl_down_sync(0xffffffffu, (uint32_t)v, d);
 }
+__device__ __forceinline__ uint64_t shfl_plane(uint64_t v, int src) { return shfl64(v, src); }
+__device__ __forceinline__ uint32_t shfl_plane(uint32_t v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+__device__ __forceinline__ uint64_t shfl_down_plane(uint64_t v, int d) { return shfl_down64(v, d); }
+__device__ __forceinline__ uint32_t shfl_down_plane(uint32_t v, int d) { return __shfl_down_sync(0xffffffffu, v, d); }
 __device__ __forceinline__ uint64_t warp_sum64(uint64_t v) {
 #pragma unroll
     for (int off = 16; off >= 1; off >>= 1) v += shfl_down64(v, off);
@@ -764,11 +809,11 @@ __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
 
 // per-sample count of set planes among the literals of the bitset `set`: bit-sliced vertical
 // counters of NB bits (count < 2^NB) per lane over the words the lane owns, then summed over
-// the lanes; returns the counts of samples lane and lane + 32
-template <int NB>
-__device__ __forceinline__ void count_planes(const uint64_t* S, const uint32_t* set, int n_words, int lane,
-                                             uint32_t& cnt0, uint32_t& cnt1) {
-    uint64_t cb[NB];
+// the lanes; returns the counts of samples lane and (64-bit planes) lane + 32
+template <int NB, typename PT>
+__device__ __forceinline__ void count_planes(const PT* S, const uint32_t* set, int n_words, int lane, uint32_t& cnt0,
+                                             uint32_t& cnt1) {
+    PT cb[NB];
 #pragma unroll
     for (int q = 0; q < NB; q++) cb[q] = 0;
     for (int w = lane; w < n_words; w += 32) {
@@ -776,10 +821,10 @@ __device__ __forceinline__ void count_planes(const uint64_t* S, const uint32_t* 
         while (bits) {
             const int bp = __ffs(bits) - 1;
             bits &= bits - 1;
-            uint64_t carry = S[32 * w + bp];
+            PT carry = S[32 * w + bp];
 #pragma unroll
             for (int q = 0; q < NB; q++) {
-                const uint64_t t = cb[q] & carry;
+                const PT t = cb[q] & carry;
                 cb[q] ^= carry;
                 carry = t;
             }
@@ -787,12 +832,12 @@ __device__ __forceinline__ void count_planes(const uint64_t* S, const uint32_t* 
     }
 #pragma unroll
     for (int off = 16; off >= 1; off >>= 1) {
-        uint64_t carry = 0;
+        PT carry = 0;
 #pragma unroll
         for (int q = 0; q < NB; q++) {
-            const uint64_t o = shfl_down64(cb[q], off);
-            const uint64_t x = cb[q] ^ o;
-            const uint64_t s = x ^ carry;
+            const PT o = shfl_down_plane(cb[q], off);
+            const PT x = cb[q] ^ o;
+            const PT s = x ^ carry;
             carry = (cb[q] & o) | (carry & x);
             cb[q] = s;
         }
@@ -800,9 +845,9 @@ __device__ __forceinline__ void count_planes(const uint64_t* S, const uint32_t* 
     cnt0 = cnt1 = 0;
 #pragma unroll
     for (int q = 0; q < NB; q++) {
-        const uint64_t t = shfl64(cb[q], 0);
-        cnt0 |= (uint32_t)((t >> lane) & 1ull) << q;
-        cnt1 |= (uint32_t)((t >> (lane + 32)) & 1ull) << q;
+        const PT t = shfl_plane(cb[q], 0);
+        cnt0 |= (uint32_t)((t >> lane) & 1u) << q;
+        if (Plane<PT>::W == 64) cnt1 |= (uint32_t)(((uint64_t)t >> (lane + 32)) & 1ull) << q;
     }
 }
 
@@ -816,12 +861,14 @@ __device__ __forceinline__ void count_planes(const uint64_t* S, const uint32_t* 
 // frontier level by level: every gate that contains the variable and every clause that contains
 // the complement of a literal that gained samples (Solver.cc:611-655), until nothing changes;
 // (4) per-sample results and integer cost accumulation;  (5) undo: clear only the planes written.
+// With 32-bit planes (1) - (5) run twice per group, once per half.
 // A point without candidates and without level-0-fixed set variables cannot start BCP at all:
 // its groups skip (1), (2), (3) and (5) - the words still stream through the ring.
-__global__ void __launch_bounds__(512, 1)
-bcp_kernel(DbDev db, BatchDev b, int warp_bytes) {
-    extern __shared__ __align__(16) unsigned char smem[];
-    __shared__ __align__(8) uint64_t blob_bar;
+template <typename PT>
+__device__ __forceinline__ void bcp_body(const DbDev& db, const BatchDev& b, int warp_bytes, unsigned char* smem,
+                                         uint64_t* blob_bar) {
+    constexpr int W = Plane<PT>::W;
+    constexpr int HALVES = 64 / W;
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int wpc = blockDim.x >> 5;
@@ -832,12 +879,12 @@ bcp_kernel(DbDev db, BatchDev b, int warp_bytes) {
     const int blob_smem_bytes = db.blob_in_smem ? (int)db.blob_bytes : 0;
     if (db.blob_in_smem) {
         if (threadIdx.x == 0) {
-            mbar_init(&blob_bar, 1);
+            mbar_init(blob_bar, 1);
             mbar_fence_init();
-            mbar_expect_tx(&blob_bar, db.blob_bytes);
+            mbar_expect_tx(blob_bar, db.blob_bytes);
             for (uint32_t off = 0; off < db.blob_bytes; off += 32768u) {
                 const uint32_t n = min(32768u, db.blob_bytes - off);
-                bulk_g2s(smem + off, db.blob + off, n, &blob_bar);
+                bulk_g2s(smem + off, db.blob + off, n, blob_bar);
             }
         }
         blob = smem;
@@ -848,24 +895,24 @@ bcp_kernel(DbDev db, BatchDev b, int warp_bytes) {
     const uint4* grec = (const uint4*)(blob + db.off_grec);
 
     unsigned char* base = smem + blob_smem_bytes + (size_t)warp * warp_bytes;
-    WarpCtx c;
-    c.S = (uint64_t*)base;
+    WarpCtx<PT> c;
+    c.S = (PT*)base;
     const int n_planes = db.n_lit + 4;
     const int inq_words = (db.n_lit + 31) >> 5;
     const int iw2 = (inq_words + 1) & ~1;
     c.fill = (uint32_t*)(c.S + n_planes);
     c.drain = c.fill + iw2;
     c.tset = c.drain + iw2;
-    c.dead = (uint64_t*)(c.tset + iw2);
+    c.dead = (PT*)(c.tset + iw2);
     // 16-byte aligned: mbarriers, then the tiles the bulk copies write
-    uint64_t* ring_bar = (uint64_t*)(base + ((((unsigned char*)(c.dead + 1) - base) + 15) & ~(size_t)15));
+    uint64_t* ring_bar = (uint64_t*)(base + ((((unsigned char*)(c.dead + 2) - base) + 15) & ~(size_t)15));
     const int stages = b.ring_stages;
     unsigned char* ring = (unsigned char*)(ring_bar + ((stages + 1) & ~1));
 
     // the planes start clean and every group cleans up after itself; pads: plane n_lit = "always
     // false" literal (FALSE plane all ones, TRUE plane 0), n_lit + 2 / + 3 = the pad variable of
     // gate records (TRUE plane 0, FALSE plane all ones: known, value 0)
-    for (int i = lane; i < n_planes; i += 32) c.S[i] = (i == db.n_lit || i == db.n_lit + 3) ? ~0ull : 0ull;
+    for (int i = lane; i < n_planes; i += 32) c.S[i] = (i == db.n_lit || i == db.n_lit + 3) ? ~(PT)0 : (PT)0;
     for (int i = lane; i < 3 * iw2; i += 32) c.fill[i] = 0;
     if (lane == 0) {
         for (int s = 0; s < stages; s++) mbar_init(&ring_bar[s], 1);
@@ -913,7 +960,7 @@ bcp_kernel(DbDev db, BatchDev b, int warp_bytes) {
 
     if (db.blob_in_smem) {
         __syncthreads();  // the barrier init is visible to everybody
-        mbar_wait(&blob_bar, 0);
+        mbar_wait(blob_bar, 0);
     }
 
     // current point, cached in registers (a warp usually stays inside one point for many groups)
@@ -939,17 +986,10 @@ bcp_kernel(DbDev db, BatchDev b, int warp_bytes) {
             flush_acc(acc, b.cost, lane);
             acc.point = p;
         }
-        const uint64_t gi = g - P_start;
-        const uint64_t s0 = gi * 64;
-        const uint64_t left = P_n_samples - s0;
-        const uint64_t valid = left >= 64 ? ~0ull : ((1ull << left) - 1);
-        const uint32_t* code = b.setcode + P_var_off;
-        const uint64_t* w = (const uint64_t*)(ring + (size_t)stage * b.ring_stage_bytes);
         // BCP can only start from a candidate record or a contradicted level-0 value (a set that
         // covers every live variable also goes the long way: its samples are models)
         const bool active = !db.unsat && (P_cand_cnt != 0 || (P_flags & POINT_HAS_FIXED) != 0 || b.assign != nullptr ||
                                           P_n_assumed == (uint32_t)db.n_live);
-
         if (!active) {
             // ---- streaming path: nothing can be implied or falsified in the groups of this
             // point.  Each tile is released as soon as it has landed; every sample has the trail
@@ -991,39 +1031,50 @@ bcp_kernel(DbDev db, BatchDev b, int warp_bytes) {
             }
             continue;
         }
-        mbar_wait_s(bar_s + (uint32_t)stage * 8u, phase);  // the group's words have landed
-        if (lane == 0) *c.dead = 0;
-        __syncwarp();
 
-        // ---- (1) assumptions (src_mpi/mpi_predicter.cpp:3236-3242: true bit => positive literal)
-        if (active) {
+        const uint64_t gi = g - P_start;
+        const uint64_t s0 = gi * 64;
+        const uint64_t left = P_n_samples - s0;
+        const uint64_t valid64 = left >= 64 ? ~0ull : ((1ull << left) - 1);
+        const uint32_t* code = b.setcode + P_var_off;
+        const uint64_t* w = (const uint64_t*)(ring + (size_t)stage * b.ring_stage_bytes);
+        mbar_wait_s(bar_s + (uint32_t)stage * 8u, phase);  // the group's words have landed
+        uint64_t dead64 = 0, full64 = 0;
+#pragma unroll 1
+        for (int half = 0; half < HALVES; half++) {
+            const PT valid = (PT)(valid64 >> (W * half));
+            if (HALVES > 1 && !valid) break;  // ragged last group: the upper half is empty
+            if (lane == 0) *c.dead = 0;
+            __syncwarp();
+
+            // ---- (1) assumptions (src_mpi/mpi_predicter.cpp:3236-3242: true bit => positive literal)
             for (uint32_t j = lane; j < k; j += 32) {
                 const uint32_t cd = j < 32 ? P_code0 : code[j];
-                const uint64_t bits = w[j];
+                const PT bits = (PT)(w[j] >> (W * half));
                 if (cd & SETCODE_FIXED) {
                     // variable already assigned at level 0: a contradicting value is a
                     // conflict (addClause_ drops the false literal: empty clause)
-                    const uint64_t bad = ((cd & 1u) ? bits : ~bits) & valid;
-                    if (bad) or64_shared(c.dead, bad);
+                    const PT bad = ((cd & 1u) ? bits : (PT)~bits) & valid;
+                    if (bad) Plane<PT>::or_shared(c.dead, bad);
                 } else {
-                    ulonglong2 tf;
+                    typename Plane<PT>::Pair tf;
                     tf.x = bits & valid;
-                    tf.y = ~bits & valid;
-                    *reinterpret_cast<ulonglong2*>(c.S + cd) = tf;  // cd is even: TRUE / FALSE pair
+                    tf.y = (PT)~bits & valid;
+                    *reinterpret_cast<typename Plane<PT>::Pair*>(c.S + cd) = tf;  // cd is even: TRUE / FALSE pair
                 }
             }
-        }
-        __syncwarp();
-        // the stage is free again: request the tile `stages` groups ahead
-        if (lane == 0) prefetch_one();
-        stage = stage + 1 == stages ? 0 : stage + 1;
-        phase ^= (stage == 0);
+            __syncwarp();
+            if (half == HALVES - 1 || !(PT)(valid64 >> (W * (HALVES - 1)))) {
+                // the stage is free again: request the tile `stages` groups ahead
+                if (lane == 0) prefetch_one();
+                stage = stage + 1 == stages ? 0 : stage + 1;
+                phase ^= (stage == 0);
+            }
 
-        uint32_t npops = 0;
-        if (active) {
+            uint32_t npops = 0;
             // ---- (2) first wave over the point's candidate records
             if (P_cand_cnt) {
-                const uint64_t live = valid & ~*(volatile uint64_t*)c.dead;
+                const PT live = valid & ~*(volatile PT*)c.dead;
                 const uint4* list = b.cand + P_cand_off;
                 uint4 r = __ldg(&list[min((uint32_t)lane, P_cand_cnt - 1)]);
                 for (uint32_t i = lane; i < P_cand_cnt; i += 32) {
@@ -1061,12 +1112,12 @@ bcp_kernel(DbDev db, BatchDev b, int warp_bytes) {
                 fetch();
                 if (!__any_sync(0xffffffffu, my_bits != 0)) break;
                 do {
-                    const uint64_t deadv = *(volatile uint64_t*)c.dead;
+                    const PT deadv = *(volatile PT*)c.dead;
                     if ((deadv & valid) == valid) {
                         stop = true;
                         break;
                     }
-                    const uint64_t live = valid & ~deadv;
+                    const PT live = valid & ~deadv;
                     const bool have = my_bits != 0;
                     uint32_t myl = 0;
                     if (have) {
@@ -1121,104 +1172,101 @@ bcp_kernel(DbDev db, BatchDev b, int warp_bytes) {
             }
             acc.pops += npops;
             __syncwarp();
-        }
 
-        // ---- (4) per-sample results
-        const uint64_t dead = *c.dead & valid;
-        const uint64_t okm = valid & ~dead;
-        uint32_t n_touched = 0;
-        if (active) {
-            // everything implied in this group: visited literals + what an early stop left behind
-            uint32_t lcnt = 0;
-            for (int wi = lane; wi < inq_words; wi += 32) {
-                const uint32_t u = c.tset[wi] | c.fill[wi] | c.drain[wi];
-                c.tset[wi] = u;
-                lcnt += __popc(u);
+            // ---- (4) per-sample results
+            const PT dead = *c.dead & valid;
+            const PT okm = valid & ~dead;
+            uint32_t n_touched = 0;
+            {
+                // everything implied in this pass: visited literals + what an early stop left behind
+                uint32_t lcnt = 0;
+                for (int wi = lane; wi < inq_words; wi += 32) {
+                    const uint32_t u = c.tset[wi] | c.fill[wi] | c.drain[wi];
+                    c.tset[wi] = u;
+                    lcnt += __popc(u);
+                }
+                n_touched = __reduce_add_sync(0xffffffffu, lcnt);
             }
-            n_touched = __reduce_add_sync(0xffffffffu, lcnt);
-        }
-        acc.touched += n_touched;
-        uint32_t cnt0, cnt1;  // assigned live variables of samples lane, lane+32
-        if (n_touched == 0 || okm == 0) {  // counts only matter for conflict-free samples
-            cnt0 = cnt1 = P_n_assumed;
-        } else {
-            // bit-sliced population count over the implied planes: per sample, how many
-            // literals of the undo set are true (each implied variable has one polarity per
-            // conflict-free sample)
-            if (n_touched < 256) count_planes<8>(c.S, c.tset, inq_words, lane, cnt0, cnt1);
-            else if (n_touched < 2048) count_planes<11>(c.S, c.tset, inq_words, lane, cnt0, cnt1);
-            else count_planes<MAX_COUNT_BITS>(c.S, c.tset, inq_words, lane, cnt0, cnt1);
-            cnt0 += P_n_assumed;
-            cnt1 += P_n_assumed;
-        }
-        const bool ok0 = (okm >> lane) & 1ull, ok1 = (okm >> (lane + 32)) & 1ull;
-        const uint32_t full_lo = __ballot_sync(0xffffffffu, ok0 && cnt0 == (uint32_t)db.n_live);
-        const uint32_t full_hi = __ballot_sync(0xffffffffu, ok1 && cnt1 == (uint32_t)db.n_live);
-        const uint64_t fullm = ((uint64_t)full_hi << 32) | full_lo;
-        const uint32_t t0 = db.n_base_assigned + cnt0, t1 = db.n_base_assigned + cnt1;
-        if (n_touched == 0 || okm == 0) {
-            const uint64_t nok = __popcll(okm);
-            acc.sum += nok * t0;
-            acc.sumsq += nok * (uint64_t)t0 * t0;
-        } else {
-            // 64-bit throughout: trail can reach n_vars, its square summed over 64 samples
-            // does not fit 32 bits from trail = 8192 on
-            const uint64_t lsum = (ok0 ? (uint64_t)t0 : 0ull) + (ok1 ? (uint64_t)t1 : 0ull);
-            const uint64_t lsq = (ok0 ? (uint64_t)t0 * t0 : 0ull) + (ok1 ? (uint64_t)t1 * t1 : 0ull);
-            const uint32_t limp = (ok0 && cnt0 > P_n_assumed ? 1 : 0) + (ok1 && cnt1 > P_n_assumed ? 1 : 0);
-            acc.sum += warp_sum64(lsum);
-            acc.sumsq += warp_sum64(lsq);
-            acc.n_impl += __reduce_add_sync(0xffffffffu, limp);
-        }
-        acc.n += __popcll(valid);
-        acc.n_conflict += __popcll(dead);
-        acc.n_full += __popcll(fullm);
+            acc.touched += n_touched;
+            uint32_t cnt0, cnt1 = 0;  // assigned live variables of samples lane, lane+32
+            if (n_touched == 0 || okm == 0) {  // counts only matter for conflict-free samples
+                cnt0 = cnt1 = P_n_assumed;
+            } else {
+                // bit-sliced population count over the implied planes: per sample, how many
+                // literals of the undo set are true (each implied variable has one polarity per
+                // conflict-free sample)
+                if (n_touched < 256) count_planes<8, PT>(c.S, c.tset, inq_words, lane, cnt0, cnt1);
+                else if (n_touched < 2048) count_planes<11, PT>(c.S, c.tset, inq_words, lane, cnt0, cnt1);
+                else count_planes<MAX_COUNT_BITS, PT>(c.S, c.tset, inq_words, lane, cnt0, cnt1);
+                cnt0 += P_n_assumed;
+                cnt1 += P_n_assumed;
+            }
+            const bool ok0 = (okm >> lane) & 1u;
+            const bool ok1 = W == 64 ? (bool)(((uint64_t)okm >> (lane + 32)) & 1ull) : false;
+            const uint32_t full_lo = __ballot_sync(0xffffffffu, ok0 && cnt0 == (uint32_t)db.n_live);
+            const uint32_t full_hi = W == 64 ? __ballot_sync(0xffffffffu, ok1 && cnt1 == (uint32_t)db.n_live) : 0u;
+            const uint64_t fullm = ((uint64_t)full_hi << 32) | full_lo;  // bits of this pass
+            const uint32_t t0 = db.n_base_assigned + cnt0, t1 = db.n_base_assigned + cnt1;
+            if (n_touched == 0 || okm == 0) {
+                const uint64_t nok = Plane<PT>::popc(okm);
+                acc.sum += nok * t0;
+                acc.sumsq += nok * (uint64_t)t0 * t0;
+            } else {
+                // 64-bit throughout: trail can reach n_vars, its square summed over 64 samples
+                // does not fit 32 bits from trail = 8192 on
+                const uint64_t lsum = (ok0 ? (uint64_t)t0 : 0ull) + (ok1 ? (uint64_t)t1 : 0ull);
+                const uint64_t lsq = (ok0 ? (uint64_t)t0 * t0 : 0ull) + (ok1 ? (uint64_t)t1 * t1 : 0ull);
+                const uint32_t limp = (ok0 && cnt0 > P_n_assumed ? 1 : 0) + (ok1 && cnt1 > P_n_assumed ? 1 : 0);
+                acc.sum += warp_sum64(lsum);
+                acc.sumsq += warp_sum64(lsq);
+                acc.n_impl += __reduce_add_sync(0xffffffffu, limp);
+            }
+            acc.n += Plane<PT>::popc(valid);
+            acc.n_conflict += Plane<PT>::popc(dead);
+            acc.n_full += __popcll(fullm);
+            dead64 |= (uint64_t)dead << (W * half);
+            full64 |= fullm << (W * half);
 
-        if (b.conflict_bits && lane == 0) {
-            b.conflict_bits[g] = dead;
-            b.full_bits[g] = fullm;
-        }
-        if (b.trail) {
-            b.trail[g * 64 + lane] = ok0 ? t0 : 0u;
-            b.trail[g * 64 + 32 + lane] = ok1 ? t1 : 0u;
-        }
-        if (b.assign) {
-            uint64_t* dst = b.assign + g * (uint64_t)db.n_lit;
-            for (int i = lane; i < db.n_lit; i += 32) dst[i] = c.S[i];
-        }
-        if (fullm) {
-            // models found by BCP alone (mpi_predicter.cpp:755-762 b_SAT_set_array)
-            uint64_t rem = fullm;
-            while (rem) {
-                const int s = __ffsll((long long)rem) - 1;
-                rem &= rem - 1;
-                unsigned long long idx = 0;
-                if (lane == 0) idx = atomicAdd(b.model_count, 1ull);
-                idx = shfl64(idx, 0);
-                if (idx < (unsigned long long)b.max_models) {
-                    for (int v0 = 0; v0 < db.n_live; v0 += 32) {
-                        const int v = v0 + lane;
-                        const uint32_t bit = v < db.n_live ? (uint32_t)((c.S[2 * v] >> s) & 1ull) : 0u;
-                        const uint32_t word = __ballot_sync(0xffffffffu, bit);
-                        if (lane == 0) b.model_bits[idx * b.model_words + (v0 >> 5)] = word;
-                    }
-                    if (lane == 0) {
-                        b.model_point[idx] = (uint32_t)p;
-                        b.model_sample[idx] = s0 + s;
+            if (b.trail) {
+                b.trail[g * 64 + W * half + lane] = ok0 ? t0 : 0u;
+                if (W == 64) b.trail[g * 64 + 32 + lane] = ok1 ? t1 : 0u;
+            }
+            if (b.assign) {
+                PT* dst = (PT*)(b.assign + g * (uint64_t)db.n_lit);  // 64-bit planes per literal; a half fills its word half
+                for (int i = lane; i < db.n_lit; i += 32) dst[(size_t)i * HALVES + half] = c.S[i];
+            }
+            if (fullm) {
+                // models found by BCP alone (mpi_predicter.cpp:755-762 b_SAT_set_array)
+                uint64_t rem = fullm;
+                while (rem) {
+                    const int s = __ffsll((long long)rem) - 1;
+                    rem &= rem - 1;
+                    unsigned long long idx = 0;
+                    if (lane == 0) idx = atomicAdd(b.model_count, 1ull);
+                    idx = shfl64(idx, 0);
+                    if (idx < (unsigned long long)b.max_models) {
+                        for (int v0 = 0; v0 < db.n_live; v0 += 32) {
+                            const int v = v0 + lane;
+                            const uint32_t bit = v < db.n_live ? (uint32_t)((c.S[2 * v] >> s) & 1u) : 0u;
+                            const uint32_t word = __ballot_sync(0xffffffffu, bit);
+                            if (lane == 0) b.model_bits[idx * b.model_words + (v0 >> 5)] = word;
+                        }
+                        if (lane == 0) {
+                            b.model_point[idx] = (uint32_t)p;
+                            b.model_sample[idx] = s0 + (uint64_t)(W * half) + s;
+                        }
                     }
                 }
             }
-        }
-        __syncwarp();
+            __syncwarp();
 
-        // ---- (5) undo: clear the assumption planes, the implied planes and the frontier bitsets
-        if (active) {
+            // ---- (5) undo: clear the assumption planes, the implied planes and the frontier bitsets
             for (uint32_t j = lane; j < k; j += 32) {
                 const uint32_t cd = j < 32 ? P_code0 : code[j];
                 if (!(cd & SETCODE_FIXED)) {
-                    ulonglong2 z;
+                    typename Plane<PT>::Pair z;
                     z.x = z.y = 0;
-                    *reinterpret_cast<ulonglong2*>(c.S + cd) = z;
+                    *reinterpret_cast<typename Plane<PT>::Pair*>(c.S + cd) = z;
                 }
             }
             if (n_touched) {
@@ -1234,8 +1282,12 @@ bcp_kernel(DbDev db, BatchDev b, int warp_bytes) {
                     c.drain[wi] = 0;
                 }
             }
+            __syncwarp();
         }
-        __syncwarp();
+        if (b.conflict_bits && lane == 0) {
+            b.conflict_bits[g] = dead64;
+            b.full_bits[g] = full64;
+        }
     }
     flush_acc(acc, b.cost, lane);
 
@@ -1264,6 +1316,19 @@ bcp_kernel(DbDev db, BatchDev b, int warp_bytes) {
             if (threadIdx.x == 0) *b.peer.cta_done = 0;
         }
     }
+}
+
+__global__ void __launch_bounds__(512, 1) bcp_kernel(DbDev db, BatchDev b, int warp_bytes) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ __align__(8) uint64_t blob_bar;
+    bcp_body<uint64_t>(db, b, warp_bytes, smem, &blob_bar);
+}
+
+// 32-bit planes: half the shared memory per warp, up to 24 warps per CTA (<= 85 registers per thread)
+__global__ void __launch_bounds__(768, 1) bcp_kernel_h(DbDev db, BatchDev b, int warp_bytes) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ __align__(8) uint64_t blob_bar;
+    bcp_body<uint32_t>(db, b, warp_bytes, smem, &blob_bar);
 }
 
 // One CTA per rank: wait until all ranks have pushed their sums for this step, publish the

@@ -31,6 +31,7 @@ static int fail(int code, const std::string& msg) {
 
 struct LaunchShape {
     int stages = 0, stage_bytes = 0, warp_bytes = 0, wpc = 0, smem_bytes = 0, blob_in_smem = 0;
+    int plane_bits = 64;  // 64: bcp_kernel, 32: bcp_kernel_h (two half passes per group)
 };
 
 struct pdsat_db {
@@ -173,23 +174,45 @@ static int count_bits_for(int n) {
 
 static constexpr int MAX_SMEM = 227 * 1024 - 128;  // the kernel also has a few bytes of static shared memory
 
-// launch shape of bcp_kernel for a batch whose largest set has kp_max (even) words per group
-static LaunchShape launch_shape(const pdsat_db* db, uint32_t kp_max) {
+// launch shape of the BCP kernel for a batch whose largest set has kp_max (even) words per group
+static LaunchShape launch_shape_bits(const pdsat_db* db, uint32_t kp_max, int plane_bits) {
     LaunchShape L;
+    L.plane_bits = plane_bits;
     L.stage_bytes = (int)kp_max * 8;
     // ~2.25 KB of tiles in flight per warp (x 12..16 warps x 148 SMs covers the HBM latency x
     // bandwidth product for the small sets); at least double buffering for the large ones
     int st = 2304 / (L.stage_bytes > 0 ? L.stage_bytes : 16);
     L.stages = st < 2 ? 2 : (st > 12 ? 12 : st);
     const int ring = ((L.stages + 1) & ~1) * 8 + L.stages * L.stage_bytes;
-    L.warp_bytes = (db->warp_bytes + ring + 15) & ~15;
+    const int pb = plane_bits / 8;
+    const int n_lit = 2 * db->host.n_live, inq_words = (n_lit + 31) / 32;
+    // planes + three bitsets (two frontiers, undo set) + the conflict mask (+ alignment slack)
+    const int state = (n_lit + 4) * pb + 3 * ((inq_words + 1) & ~1) * 4 + 2 * pb + 16;
+    L.warp_bytes = (state + ring + 15) & ~15;
     const int blob = (int)db->host.blob.size();
     L.blob_in_smem = (blob <= 64 * 1024 && blob + L.warp_bytes <= MAX_SMEM) ? 1 : 0;
     int wpc = (MAX_SMEM - (L.blob_in_smem ? blob : 0)) / L.warp_bytes;
-    if (wpc > 16) wpc = 16;  // __launch_bounds__(512)
+    const int cap = plane_bits == 64 ? 16 : 24;  // __launch_bounds__(512) / (768)
+    if (wpc > cap) wpc = cap;
     L.wpc = wpc;
     L.smem_bytes = wpc * L.warp_bytes + (L.blob_in_smem ? blob : 0);
     return L;
+}
+
+// 64-bit planes (one pass per 64-sample group) unless the per-warp state is so large that fewer
+// than 4 warps fit an SM: then half-size planes (two passes per group) multiply the resident warps.
+// Measured (B200, profiles/r02_plane_width.md): A5/2 (7 087 live variables, 1 -> 3 warps) 1.46x
+// faster with half planes; ODLS (5 -> 11 warps) and Bivium (16 -> 24) slower, because a literal
+// implied in both halves is visited twice (ODLS: 1.97x the literal visits).
+// PDSAT_PLANE_BITS=32|64 overrides (experiments, before/after profiles).
+static LaunchShape launch_shape(const pdsat_db* db, uint32_t kp_max) {
+    const char* e = getenv("PDSAT_PLANE_BITS");
+    const int forced = e ? atoi(e) : 0;
+    if (forced == 32 || forced == 64) return launch_shape_bits(db, kp_max, forced);
+    const LaunchShape L64 = launch_shape_bits(db, kp_max, 64);
+    if (L64.wpc >= 4) return L64;
+    const LaunchShape L32 = launch_shape_bits(db, kp_max, 32);
+    return L32.wpc > L64.wpc ? L32 : L64;
 }
 
 // (re)build the device copy + launch shape from db->host
@@ -201,12 +224,9 @@ static int sync_device_db(pdsat_db* db) {
     if (count_bits_for(h.n_live) > MAX_COUNT_BITS) return fail(PDSAT_ERR_LIMIT, "too many live variables for the counters");
     int n_lit = 2 * h.n_live;
     int n_planes = n_lit + 4;
-    int inq_words = (n_lit + 31) / 32;
-    // planes + three bitsets (two frontiers, undo set) + the conflict mask
-    int warp_bytes = n_planes * 8 + 3 * ((inq_words + 1) & ~1) * 4 + 8;
-    warp_bytes = (warp_bytes + 15) & ~15;
+    (void)n_planes;
     db->qcap = 0;
-    db->warp_bytes = warp_bytes;
+    db->warp_bytes = 0;
     if (db->device < 0) {
         db->warps_per_cta = 0;
         return PDSAT_OK;
@@ -243,6 +263,7 @@ static int sync_device_db(pdsat_db* db) {
     db->dev.n_gates = (int32_t)h.gates.size();
     db->dev.n_rec = (int32_t)h.n_rec;
     CU(cudaFuncSetAttribute(bcp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM));
+    CU(cudaFuncSetAttribute(bcp_kernel_h, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM));
     return PDSAT_OK;
 }
 
@@ -927,7 +948,8 @@ int pdsat_batch_propagate(pdsat_batch* b) {
         bd.peer.parity = parity;
         bd.peer.n_words = n_cost_words;
     }
-    bcp_kernel<<<grid, L.wpc * 32, L.smem_bytes, st>>>(dev, bd, L.warp_bytes);
+    if (L.plane_bits == 64) bcp_kernel<<<grid, L.wpc * 32, L.smem_bytes, st>>>(dev, bd, L.warp_bytes);
+    else bcp_kernel_h<<<grid, L.wpc * 32, L.smem_bytes, st>>>(dev, bd, L.warp_bytes);
     b->n_kernels++;
     if (b->peer_ranks > 0) {
         const unsigned long long target = (unsigned long long)(b->peer_step / 2 + 1) * b->peer_ranks;
