@@ -593,6 +593,37 @@ def run_ours(args):
         dist.barrier()
     batch.close()
 
+    # ---------------- the same e2e sequence with the declared counter-based generator
+    # (PDSAT_MODE_RANDOM_COUNTER: NOT the reference's stream; for callers that only need i.i.d. bits)
+    bc = api.Batch(db, [api.Point(SET_VARS, n, api.MODE_COUNTER, seed=seed0, first_sample=(first + 63) // 64 * 64)])
+    cost_c = torch.zeros(api.COST_WORDS, dtype=torch.int64, device="cuda")
+    bc.set_cost_buffer(cost_c.data_ptr())
+    mode_c = "none"
+    if dist is not None:
+        mode_c = connect_peers(torch, dist, bc, rank, world, args.reduce)
+    for w in range(3):
+        bc.reseed(0, seed0 + w, (first + 63) // 64 * 64)
+        bc.fill()
+        bc.propagate()
+        if mode_c == "nccl":
+            dist.all_reduce(cost_c)
+        bc.costs()
+    barrier()
+    t0 = time.perf_counter()
+    for s in range(args.steps):
+        bc.reseed(0, seed0 + 104729 * (s + 1), (first + 63) // 64 * 64)
+        bc.fill()
+        bc.propagate()
+        if mode_c == "nccl":
+            dist.all_reduce(cost_c)
+        cc = bc.costs()[0]
+    barrier()
+    e2e_counter_s = time.perf_counter() - t0
+    fill_c_ms, _ = bc.last_ms()
+    if dist is not None:
+        dist.barrier()
+    bc.close()
+
     prof = load_profile_metrics()
     info = db.info()
     extra = {}
@@ -650,10 +681,10 @@ def run_ours(args):
             extra["tabu_step"] = extra_tabu
             extra["solve_a52"] = extra_solve
 
-    t = torch.tensor([dev_ms, e2e_s * 1e3, float(kernel_ms)], dtype=torch.float64, device="cuda")
+    t = torch.tensor([dev_ms, e2e_s * 1e3, float(kernel_ms), e2e_counter_s * 1e3], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms, kernel_ms = (float(x) for x in t.tolist())
+    dev_ms, e2e_ms, kernel_ms, e2e_counter_ms = (float(x) for x in t.tolist())
 
     if rank == 0:
         total = n * world * args.steps
@@ -686,8 +717,14 @@ def run_ours(args):
             "propagated_literals_per_s": value * len(SET_VARS),
             "e2e": {"value": e2e_value, "unit": "samples/s",
                     "h2d_bytes_per_step": int(h2d_per_step), "d2h_bytes_per_step": 8 * api.COST_WORDS,
+                    "ms_per_step": e2e_ms / args.steps, "fill_ms": fill_ms_last,
+                    "generator": "mt19937 + bool_rand in the reference's 1-worker order (device jump-ahead)",
                     "note": "inputs are descriptors (set, seed, window): sample values are generated on the "
-                            "device; H2D = point descriptors + generator seed state + jump plan"},
+                            "device; H2D = point descriptors + generator seed state + jump plan",
+                    "counter_generator": {"value": total / (e2e_counter_ms * 1e-3), "ms_per_step": e2e_counter_ms / args.steps,
+                                          "fill_ms": fill_c_ms, "n_check": int(cc.n),
+                                          "note": "same call sequence with PDSAT_MODE_RANDOM_COUNTER (declared "
+                                                  "splitmix64 generator, not the reference stream)"}},
             "gpu_launches": int(gpu_launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,

@@ -202,10 +202,13 @@ int pdsat_batch_costs(pdsat_batch* b, pdsat_cost* out /* n_points */);
 
 /* Multi-GPU, one process per GPU: cost all-reduce FUSED into the BCP kernel over NVLink peer
  * memory instead of a separate collective.  Every rank exports a 64-byte CUDA IPC handle of its
- * reduce buffer, the ranks exchange the handles out of band (all_gather of 64 bytes), every
+ * receive buffer, the ranks exchange the handles out of band (all_gather of 64 bytes), every
  * rank connects; from then on pdsat_batch_propagate is COLLECTIVE (all ranks must call it the
  * same number of times) and leaves the summed accumulators of ALL ranks in the cost buffer.
- * Replaces the ncclAllReduce of SURVEY.md 8(e); results are identical (integer sums). */
+ * Inside the kernel: the last CTA stores the rank's sums as tagged 8-byte packets into every
+ * peer's buffer and gathers the peers' packets from its own (no fence, no atomics, no second
+ * kernel).  Replaces the ncclAllReduce of SURVEY.md 8(e); results are identical (integer sums).
+ * Use it with one rank per GPU only: ranks that wait for each other must run concurrently. */
 #define PDSAT_IPC_HANDLE_BYTES 64
 int pdsat_batch_peer_export(pdsat_batch* b, void* handle_out /* 64 bytes */);
 int pdsat_batch_peer_connect(pdsat_batch* b, int32_t n_ranks, int32_t my_rank,

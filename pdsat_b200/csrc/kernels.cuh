@@ -63,21 +63,28 @@ static constexpr uint32_t POINT_HAS_FIXED = 1u;  // some set variable is assigne
 
 static constexpr uint32_t SETCODE_FIXED = 0x80000000u;  // set var already assigned at level 0; bit0 = its lbool
 
-// Multi-GPU cost reduce fused into the BCP kernel.  Every rank owns a small buffer that its
-// peers map through CUDA IPC: shared[parity][n_words] accumulators + done[parity] counters.
-// The last CTA of a rank's kernel adds the rank's per-point sums into EVERY rank's buffer with
-// system-scope atomics over NVLink and then signals done[parity] on every rank; a one-CTA
-// kernel on each rank waits for n_ranks signals and copies the all-reduced sums out.  Buffers
-// alternate by step parity, so a rank that runs ahead never touches the buffer a slower rank
-// is still reading (it cannot get two steps ahead: its own wait needs the slower rank's step).
+// Multi-GPU cost reduce fused into the BCP kernel (an all-gather + local sum over NVLink peer
+// memory).  Every rank owns a receive buffer that its peers map through CUDA IPC:
+//     recv[parity][source rank][2 * n_words] packets of 8 bytes = {uint32 data, uint32 tag}
+// (each 64-bit accumulator travels as two packets).  The last CTA of a rank's kernel stores the
+// rank's per-point sums, tagged with the step number, into its slot of EVERY rank's buffer with
+// plain 8-byte stores - a naturally aligned 8-byte store is delivered whole, so a packet whose
+// tag matches carries valid data: no fence, no flag, no atomics, and stale packets of older
+// steps never match, so nothing is ever cleared (the scheme of NCCL's LL protocol).  The SAME CTA
+// then polls its own buffer until all ranks' packets of this step are in, adds them in rank
+// order (integers: any order gives the same sum) and publishes the totals - there is no second
+// kernel.  Buffers alternate by step parity, so a rank that runs ahead never overwrites packets
+// a slower rank is still reading (it cannot get two steps ahead: its own gather needs the
+// slower rank's packets of the step in between).
 static constexpr int MAX_PEERS = 16;
 struct PeerDev {
-    unsigned long long* shared[MAX_PEERS];  // rank r's buffer as mapped in this process
+    unsigned long long* shared[MAX_PEERS];  // rank r's receive buffer as mapped in this process
     unsigned int* cta_done;                 // local ticket counter (last-CTA detection)
     int32_t n_ranks;
     int32_t me;
     int32_t parity;
-    int32_t n_words;                        // accumulators per parity = n_points * 8
+    int32_t n_words;                        // accumulators = n_points * 8
+    uint32_t tag;                           // step number + 1 (never 0)
 };
 
 struct BatchDev {
@@ -1292,7 +1299,7 @@ __device__ __forceinline__ void bcp_body(const DbDev& db, const BatchDev& b, int
     flush_acc(acc, b.cost, lane);
 
     if (b.peer.n_ranks > 0) {
-        // last CTA of this rank pushes the rank's sums to every peer (itself included)
+        // the last CTA of this rank exchanges the rank's sums with every peer (see PeerDev)
         __shared__ unsigned int s_ticket;
         __threadfence();
         __syncthreads();
@@ -1300,19 +1307,34 @@ __device__ __forceinline__ void bcp_body(const DbDev& db, const BatchDev& b, int
         __syncthreads();
         if (s_ticket == gridDim.x - 1) {
             __threadfence();
-            const int nw = b.peer.n_words, nr = b.peer.n_ranks;
-            // one fire-and-forget reduction per (word, rank); each rank starts with a different
-            // target so that the ranks do not all hit the same peer at the same moment
-            for (int j = threadIdx.x; j < nw * nr; j += blockDim.x) {
-                const int i = j % nw;
-                const int r = (j / nw + b.peer.me) % nr;
-                const unsigned long long v = __ldcg(&b.cost[i]);
-                if (v) atomicAdd_system(&b.peer.shared[r][(size_t)b.peer.parity * nw + i], v);
+            const int nw = b.peer.n_words, nr = b.peer.n_ranks, me = b.peer.me;
+            const uint32_t tag = b.peer.tag;
+            const size_t slot = ((size_t)b.peer.parity * MAX_PEERS + me) * 2 * nw;  // my slot in a receive buffer
+            // push: packet e of my slot on rank r; every rank starts with a different target so
+            // that the ranks do not all hit the same peer at the same moment
+            for (int j = threadIdx.x; j < 2 * nw * nr; j += blockDim.x) {
+                const int e = j % (2 * nw);
+                const int r = (j / (2 * nw) + me) % nr;
+                const unsigned long long v = __ldcg(&b.cost[e >> 1]);
+                const unsigned long long pkt = ((unsigned long long)tag << 32) | (uint32_t)((e & 1) ? (v >> 32) : v);
+                *((volatile unsigned long long*)&b.peer.shared[r][slot + e]) = pkt;
             }
-            __threadfence_system();
-            __syncthreads();
-            if (threadIdx.x < nr)
-                atomicAdd_system(&b.peer.shared[(threadIdx.x + b.peer.me) % nr][(size_t)2 * nw + b.peer.parity], 1ull);
+            __syncthreads();  // all of my sums are on their way before b.cost is overwritten
+            // gather: wait for this step's packets of every rank in my own buffer, add, publish
+            const volatile unsigned long long* mine = b.peer.shared[me] + (size_t)b.peer.parity * MAX_PEERS * 2 * nw;
+            for (int i = threadIdx.x; i < nw; i += blockDim.x) {
+                unsigned long long sum = 0;
+                for (int src = 0; src < nr; src++) {
+                    const volatile unsigned long long* q = mine + (size_t)src * 2 * nw + 2 * i;
+                    unsigned long long lo, hi;
+                    do lo = q[0];
+                    while ((uint32_t)(lo >> 32) != tag);
+                    do hi = q[1];
+                    while ((uint32_t)(hi >> 32) != tag);
+                    sum += (hi << 32) | (uint32_t)lo;
+                }
+                b.cost[i] = sum;
+            }
             if (threadIdx.x == 0) *b.peer.cta_done = 0;
         }
     }
@@ -1329,23 +1351,6 @@ __global__ void __launch_bounds__(768, 1) bcp_kernel_h(DbDev db, BatchDev b, int
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ __align__(8) uint64_t blob_bar;
     bcp_body<uint32_t>(db, b, warp_bytes, smem, &blob_bar);
-}
-
-// One CTA per rank: wait until all ranks have pushed their sums for this step, publish the
-// all-reduced accumulators and clear the parity buffer for its next use (two steps later).
-__global__ void peer_wait_kernel(unsigned long long* shared, int n_words, int parity, unsigned long long target,
-                                 unsigned long long* cost_out) {
-    volatile unsigned long long* done = shared + (size_t)2 * n_words + parity;
-    if (threadIdx.x == 0) {
-        while (*done < target) __nanosleep(50);
-        __threadfence_system();
-    }
-    __syncthreads();
-    unsigned long long* buf = shared + (size_t)parity * n_words;
-    for (int i = threadIdx.x; i < n_words; i += blockDim.x) {
-        cost_out[i] = *((volatile unsigned long long*)&buf[i]);
-        buf[i] = 0;
-    }
 }
 
 }  // namespace pdsat

@@ -947,16 +947,12 @@ int pdsat_batch_propagate(pdsat_batch* b) {
         bd.peer.me = b->peer_me;
         bd.peer.parity = parity;
         bd.peer.n_words = n_cost_words;
+        bd.peer.tag = (uint32_t)(b->peer_step + 1);
     }
     if (L.plane_bits == 64) bcp_kernel<<<grid, L.wpc * 32, L.smem_bytes, st>>>(dev, bd, L.warp_bytes);
     else bcp_kernel_h<<<grid, L.wpc * 32, L.smem_bytes, st>>>(dev, bd, L.warp_bytes);
     b->n_kernels++;
-    if (b->peer_ranks > 0) {
-        const unsigned long long target = (unsigned long long)(b->peer_step / 2 + 1) * b->peer_ranks;
-        peer_wait_kernel<<<1, 256, 0, st>>>(b->d_peer_own, n_cost_words, parity, target, cost);
-        b->n_kernels++;
-        b->peer_step++;
-    }
+    if (b->peer_ranks > 0) b->peer_step++;  // the exchange happens inside the kernel (its last CTA)
     CU(cudaGetLastError());
     CU(cudaEventRecord(b->ev[3], st));
     b->propagated = true;
@@ -1099,7 +1095,8 @@ int pdsat_batch_peer_export(pdsat_batch* b, void* handle_out) {
     if (!b || !handle_out) return fail(PDSAT_ERR_ARG, "pdsat_batch_peer_export: bad argument");
     static_assert(sizeof(cudaIpcMemHandle_t) == PDSAT_IPC_HANDLE_BYTES, "IPC handle size");
     CU(cudaSetDevice(b->db->device));
-    const size_t words = 2 * (size_t)PDSAT_COST_WORDS * b->pts.size() + 2;
+    // receive buffer: [parity][source rank][2 packets per accumulator] (kernels.cuh PeerDev)
+    const size_t words = 2 * (size_t)MAX_PEERS * 2 * (size_t)PDSAT_COST_WORDS * b->pts.size();
     if (!b->d_peer_own) {
         CU(cudaMalloc(&b->d_peer_own, sizeof(unsigned long long) * words));
         CU(cudaMemset(b->d_peer_own, 0, sizeof(unsigned long long) * words));
@@ -1128,6 +1125,10 @@ int pdsat_batch_peer_connect(pdsat_batch* b, int32_t n_ranks, int32_t my_rank, c
         CU(cudaIpcOpenMemHandle(&p, hd, cudaIpcMemLazyEnablePeerAccess));
         b->peer_ptr[r] = (unsigned long long*)p;
     }
+    // the step tags restart at 1: packets of an earlier connection must not match them.  The
+    // caller synchronises the ranks (a barrier) between connect and the first propagate.
+    const size_t words = 2 * (size_t)MAX_PEERS * 2 * (size_t)PDSAT_COST_WORDS * b->pts.size();
+    CU(cudaMemset(b->d_peer_own, 0, sizeof(unsigned long long) * words));
     b->peer_ranks = n_ranks;
     b->peer_me = my_rank;
     b->peer_step = 0;
