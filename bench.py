@@ -569,10 +569,57 @@ def run_ours(args):
             dist.all_reduce(cost_t)
         c = batch.costs()[0]
     barrier()
-    e2e_s = time.perf_counter() - t0
+    e2e_serial_s = time.perf_counter() - t0
     n_reduced_check = c.n
     fill_ms_last, _ = batch.last_ms()
     h2d_per_step = batch.h2d_bytes()
+
+    # ---------------- e2e, pipelined: the same call sequence with `depth` batches in flight (one
+    # database handle + stream each, round robin); every step still uploads its own descriptors and
+    # reads its own 64-byte result back, the read of step s waits only for step s.  The stages of a
+    # step (jump tree, bit generator, transpose, BCP) are latency-bound kernels with small grids:
+    # steps that overlap fill each other's idle issue slots.
+    depth = max(1, args.pipeline if dist is None else min(args.pipeline, 2))
+    lanes = []
+    for d in range(depth):
+        if d == 0:
+            lanes.append((db, batch, cost_t))
+            continue
+        db_d = api.ClauseDb(nv, offs, lits, device=local_rank)
+        db_d.set_fixed_assumptions(stream)
+        st_d = torch.cuda.Stream()
+        db_d.set_stream(st_d.cuda_stream)
+        b_d = api.Batch(db_d, [api.Point(SET_VARS, n, api.MODE_MT19937, seed=seed0, first_sample=first)])
+        c_d = torch.zeros(api.COST_WORDS, dtype=torch.int64, device="cuda")
+        b_d.set_cost_buffer(c_d.data_ptr())
+        if dist is not None:
+            m_d = connect_peers(torch, dist, b_d, rank, world, args.reduce)
+            assert m_d == reduce_mode
+        lanes.append((db_d, b_d, c_d, st_d))
+
+    def pipelined(n_steps, seed_mul):
+        last = None
+        for s in range(n_steps):
+            ln = lanes[s % depth]
+            if s >= depth:
+                last = ln[1].costs()[0]  # result of the step that used this lane `depth` steps ago
+            ln[1].reseed(0, seed0 + seed_mul * (s + 1), first)
+            ln[1].fill()
+            ln[1].propagate()
+            if use_nccl:
+                with torch.cuda.stream(ln[3] if len(ln) > 3 else stream_t):
+                    dist.all_reduce(ln[2])
+        for s in range(max(0, n_steps - depth), n_steps):
+            last = lanes[s % depth][1].costs()[0]
+        return last
+
+    pipelined(2 * depth, 7919)
+    barrier()
+    t0 = time.perf_counter()
+    c_p = pipelined(args.steps, 15485863)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    n_pipe_check = c_p.n
     # the timed regions above last milliseconds; keep the same fill+propagate load running for
     # ~1.5 s more so that nvidia-smi (100 ms period) sees the clocks under this load
     t_probe = time.perf_counter()
@@ -591,6 +638,12 @@ def run_ours(args):
     clocks["note"] = "sampled across the timed regions plus 1.5 s of the same fill+propagate load"
     if dist is not None:
         dist.barrier()
+    for ln in lanes[1:]:
+        ln[1].close()
+    if dist is not None:
+        dist.barrier()
+    for ln in lanes[1:]:
+        ln[0].close()
     batch.close()
 
     # ---------------- the same e2e sequence with the declared counter-based generator
@@ -681,10 +734,11 @@ def run_ours(args):
             extra["tabu_step"] = extra_tabu
             extra["solve_a52"] = extra_solve
 
-    t = torch.tensor([dev_ms, e2e_s * 1e3, float(kernel_ms), e2e_counter_s * 1e3], dtype=torch.float64, device="cuda")
+    t = torch.tensor([dev_ms, e2e_s * 1e3, float(kernel_ms), e2e_counter_s * 1e3, e2e_serial_s * 1e3], dtype=torch.float64,
+                     device="cuda")
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms, kernel_ms, e2e_counter_ms = (float(x) for x in t.tolist())
+    dev_ms, e2e_ms, kernel_ms, e2e_counter_ms, e2e_serial_ms = (float(x) for x in t.tolist())
 
     if rank == 0:
         total = n * world * args.steps
@@ -718,9 +772,14 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": "samples/s",
                     "h2d_bytes_per_step": int(h2d_per_step), "d2h_bytes_per_step": 8 * api.COST_WORDS,
                     "ms_per_step": e2e_ms / args.steps, "fill_ms": fill_ms_last,
+                    "pipeline_depth": depth, "n_check": int(n_pipe_check),
+                    "serial": {"value": total / (e2e_serial_ms * 1e-3), "ms_per_step": e2e_serial_ms / args.steps,
+                               "note": "one step at a time: reseed -> fill -> propagate -> costs() before the next"},
                     "generator": "mt19937 + bool_rand in the reference's 1-worker order (device jump-ahead)",
                     "note": "inputs are descriptors (set, seed, window): sample values are generated on the "
-                            "device; H2D = point descriptors + generator seed state + jump plan",
+                            "device; H2D = point descriptors + generator seed state + jump plan.  `pipeline_depth` "
+                            "steps are in flight (one handle + stream each); every step uploads its own descriptors "
+                            "and reads its own result",
                     "counter_generator": {"value": total / (e2e_counter_ms * 1e-3), "ms_per_step": e2e_counter_ms / args.steps,
                                           "fill_ms": fill_c_ms, "n_check": int(cc.n),
                                           "note": "same call sequence with PDSAT_MODE_RANDOM_COUNTER (declared "
@@ -807,6 +866,7 @@ def main():
     ap.add_argument("--cascade", type=lambda v: [int(x) for x in v.split(",") if x], default=[86, 90, 100, 120, 177],
                     help="set sizes (bivium_Ending2 prefixes) of the timed + parity-checked cascade legs")
     ap.add_argument("--cascade-samples", type=int, default=1_000_000)
+    ap.add_argument("--pipeline", type=int, default=8, help="steps in flight in the e2e measurement (1 GPU; 2 when N > 1)")
     ap.add_argument("--tabu-samples", type=int, default=1_000_000, help="samples per point of the tabu-step leg")
     ap.add_argument("--a52-known", type=int, default=32, help="known R1|R2|R3 bits of the A5/2 solve leg (set = 64 - known)")
     ap.add_argument("--solve-check-bits", type=int, default=18, help="log2 size of the slice checked against the CPU")
