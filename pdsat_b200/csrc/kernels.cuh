@@ -1164,14 +1164,24 @@ __device__ __forceinline__ void bcp_body(const DbDev& db, const BatchDev& b, int
                         const uint32_t cum = warp_incl_scan(clen, lane);
                         const uint32_t total = __shfl_sync(0xffffffffu, cum, 31);
                         const uint32_t cbase = cbeg - (cum - clen);
+                        // the record of the NEXT trip is requested before this trip's clause is
+                        // evaluated: the L2 round trip of the occurrence lists hides behind the work
+                        uint4 r_next = make_uint4(0, 0, 0, 0);
+                        {
+                            const int q = find_owner(cum, (uint32_t)lane);
+                            const uint32_t bq = __shfl_sync(0xffffffffu, cbase, q & 31);
+                            if ((uint32_t)lane < total) r_next = __ldg(&db.occrec[bq + lane]);
+                        }
                         for (uint32_t i0 = 0; i0 < total; i0 += 32) {
                             const uint32_t i = i0 + lane;
-                            const int q = find_owner(cum, i);
-                            const uint32_t bq = __shfl_sync(0xffffffffu, cbase, q & 31);
-                            if (i < total) {
-                                const uint4 r = __ldg(&db.occrec[bq + i]);
-                                eval_clause(r, db.rec, c, live, pad2);
+                            const uint4 r = r_next;
+                            if (i0 + 32 < total) {
+                                const uint32_t in = i + 32;
+                                const int q = find_owner(cum, in);
+                                const uint32_t bq = __shfl_sync(0xffffffffu, cbase, q & 31);
+                                if (in < total) r_next = __ldg(&db.occrec[bq + in]);
                             }
+                            if (i < total) eval_clause(r, db.rec, c, live, pad2);
                         }
                     }
                     __syncwarp();
