@@ -84,7 +84,15 @@ struct HostDb {
     std::vector<uint32_t> occ_off;        // 2*n_live + 1
     std::vector<uint32_t> occ;            // record index of each clause containing the literal
     std::vector<uint16_t> rec_len;        // clause length, indexed by its first record
-    std::vector<uint16_t> occrec;         // per literal (occ_off): the records themselves, inline
+    std::vector<uint16_t> occrec;         // per literal (docc_off): the records of its SHORT clauses, inline
+    std::vector<uint32_t> docc_off;       // 2*n_live + 1: device occurrence offsets (short clauses only)
+    // long clauses (> 8 literals) are visited lazily: per literal the ids of the long clauses that
+    // contain it; the device marks them when the literal is falsified and evaluates every marked
+    // clause ONCE when the frontier is empty (instead of at every falsification)
+    std::vector<uint32_t> long_rec;       // id -> first record of the chain in rec
+    std::vector<uint32_t> locc_off;       // 2*n_live + 1
+    std::vector<uint16_t> locc;           // long clause ids
+    bool lazy_long = false;
     // gates
     std::vector<HostGate> gates;
     std::vector<uint16_t> gate_rec;       // n_gates * 8 slots
@@ -93,7 +101,7 @@ struct HostDb {
     int64_t n_gate_clauses = 0;           // clauses replaced by gates
     // index blob staged into shared memory by the kernel (16-byte aligned sections)
     std::vector<uint8_t> blob;
-    uint32_t blob_occ_off = 0, blob_gocc_off = 0, blob_gocc = 0, blob_grec = 0;
+    uint32_t blob_occ_off = 0, blob_gocc_off = 0, blob_gocc = 0, blob_grec = 0, blob_locc_off = 0, blob_locc = 0, blob_lrec = 0;
     int64_t n_rec = 0;
     int64_t n_clauses_live = 0;
     int64_t n_lits_live = 0;
@@ -364,6 +372,11 @@ struct HostDb {
         occ_off.assign((size_t)2 * n_live + 1, 0);
         occ.clear();
         occrec.clear();
+        docc_off.assign((size_t)2 * n_live + 1, 0);
+        locc_off.assign((size_t)2 * n_live + 1, 0);
+        locc.clear();
+        long_rec.clear();
+        lazy_long = false;
         gates.clear();
         gate_rec.clear();
         gocc_off.assign((size_t)n_live + 1, 0);
@@ -434,8 +447,32 @@ struct HostDb {
             for (size_t l = 0; l < (size_t)2 * n_live; l++)
                 std::stable_sort(occ.begin() + occ_off[l], occ.begin() + occ_off[l + 1],
                                  [&](uint32_t x, uint32_t y) { return rec_len[x] < rec_len[y]; });
-            occrec.resize(occ.size() * REC_SLOTS);
-            for (size_t i = 0; i < occ.size(); i++) inline_record(occ[i], &occrec[i * REC_SLOTS]);
+            // device lists: short clauses inline; long clauses by id (lazy) when their ids fit 16 bits
+            size_t n_long = 0;
+            for (size_t r = 0; r < rec_len.size(); r++)
+                if (rec_len[r] > REC_SLOTS) n_long++;
+            lazy_long = n_long > 0 && n_long < 0xFFFF && !getenv("PDSAT_NO_LAZY_LONG");
+            std::vector<uint32_t> long_id(rec_len.size(), 0);
+            if (lazy_long)
+                for (size_t r = 0; r < rec_len.size(); r++)
+                    if (rec_len[r] > REC_SLOTS) {
+                        long_id[r] = (uint32_t)long_rec.size();
+                        long_rec.push_back((uint32_t)r);
+                    }
+            docc_off.assign((size_t)2 * n_live + 1, 0);
+            locc_off.assign((size_t)2 * n_live + 1, 0);
+            std::vector<uint32_t> docc;
+            for (size_t l = 0; l < (size_t)2 * n_live; l++) {
+                for (uint32_t o = occ_off[l]; o < occ_off[l + 1]; o++) {
+                    const uint32_t r = occ[o];
+                    if (lazy_long && rec_len[r] > REC_SLOTS) locc.push_back((uint16_t)long_id[r]);
+                    else docc.push_back(r);
+                }
+                docc_off[l + 1] = (uint32_t)docc.size();
+                locc_off[l + 1] = (uint32_t)locc.size();
+            }
+            occrec.resize(docc.size() * REC_SLOTS);
+            for (size_t i = 0; i < docc.size(); i++) inline_record(docc[i], &occrec[i * REC_SLOTS]);
             // gates: records + per-variable lists
             gate_rec.resize(gates.size() * REC_SLOTS);
             std::vector<std::pair<uint32_t, uint32_t>> gp;  // (live var, gate)
@@ -453,17 +490,26 @@ struct HostDb {
             std::vector<uint32_t> gpos(gocc_off.begin(), gocc_off.end() - 1);
             for (auto& pr : gp) gocc[gpos[pr.first]++] = (uint16_t)pr.second;
         }
-        // index blob: [occ_off][gocc_off][gocc][gate records], sections 16-byte aligned
+        // index blob: [occ offsets (short clauses)][gocc_off][gocc][gate records][locc_off][locc]
+        // [long_rec], sections 16-byte aligned; the long-clause sections only when there are any
         auto align16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
         blob_occ_off = 0;
-        blob_gocc_off = (uint32_t)align16(occ_off.size() * 4);
+        blob_gocc_off = (uint32_t)align16(docc_off.size() * 4);
         blob_gocc = (uint32_t)align16(blob_gocc_off + gocc_off.size() * 4);
         blob_grec = (uint32_t)align16(blob_gocc + gocc.size() * 2);
-        blob.assign(align16(blob_grec + gate_rec.size() * 2), 0);
-        memcpy(blob.data() + blob_occ_off, occ_off.data(), occ_off.size() * 4);
+        blob_locc_off = (uint32_t)align16(blob_grec + gate_rec.size() * 2);
+        blob_locc = (uint32_t)align16(blob_locc_off + (lazy_long ? locc_off.size() * 4 : 0));
+        blob_lrec = (uint32_t)align16(blob_locc + locc.size() * 2);
+        blob.assign(align16(blob_lrec + long_rec.size() * 4), 0);
+        memcpy(blob.data() + blob_occ_off, docc_off.data(), docc_off.size() * 4);
         memcpy(blob.data() + blob_gocc_off, gocc_off.data(), gocc_off.size() * 4);
         if (!gocc.empty()) memcpy(blob.data() + blob_gocc, gocc.data(), gocc.size() * 2);
         if (!gate_rec.empty()) memcpy(blob.data() + blob_grec, gate_rec.data(), gate_rec.size() * 2);
+        if (lazy_long) {
+            memcpy(blob.data() + blob_locc_off, locc_off.data(), locc_off.size() * 4);
+            memcpy(blob.data() + blob_locc, locc.data(), locc.size() * 2);
+            memcpy(blob.data() + blob_lrec, long_rec.data(), long_rec.size() * 4);
+        }
     }
 
     // the 16-byte record a list holds for the clause whose chain starts at rec[r]

@@ -29,14 +29,15 @@ struct DbDev {
     // [gate records uint4[]], sections 16-byte aligned; staged into shared memory when it fits
     const unsigned char* blob;
     uint32_t blob_bytes;
-    uint32_t off_gocc_off, off_gocc, off_grec;
+    uint32_t off_gocc_off, off_gocc, off_grec, off_locc_off, off_locc, off_lrec;
     int32_t blob_in_smem;
     int32_t n_live;
     int32_t n_lit;            // 2*n_live
     int32_t n_base_assigned;
     int32_t unsat;            // level-0 conflict: every sample is a conflict
     int32_t n_gates;
-    int32_t n_rec;            // clause records (0: every clause lives in a gate)
+    int32_t n_rec;            // short-clause occurrence entries (0: no clause phase)
+    int32_t n_long;           // long clauses handled lazily (0: none)
 };
 
 struct PointDev {
@@ -900,6 +901,9 @@ __device__ __forceinline__ void bcp_body(const DbDev& db, const BatchDev& b, int
     const uint32_t* gocc_off = (const uint32_t*)(blob + db.off_gocc_off);
     const uint16_t* gocc = (const uint16_t*)(blob + db.off_gocc);
     const uint4* grec = (const uint4*)(blob + db.off_grec);
+    const uint32_t* locc_off = (const uint32_t*)(blob + db.off_locc_off);
+    const uint16_t* locc = (const uint16_t*)(blob + db.off_locc);
+    const uint32_t* lrec = (const uint32_t*)(blob + db.off_lrec);
 
     unsigned char* base = smem + blob_smem_bytes + (size_t)warp * warp_bytes;
     WarpCtx<PT> c;
@@ -910,7 +914,11 @@ __device__ __forceinline__ void bcp_body(const DbDev& db, const BatchDev& b, int
     c.fill = (uint32_t*)(c.S + n_planes);
     c.drain = c.fill + iw2;
     c.tset = c.drain + iw2;
-    c.dead = (PT*)(c.tset + iw2);
+    // marks of the long clauses whose literals were falsified since they were last evaluated
+    uint32_t* lmark = c.tset + iw2;
+    const int lm_words = (db.n_long + 31) >> 5;
+    const int lm2 = (lm_words + 1) & ~1;
+    c.dead = (PT*)(lmark + lm2);
     // 16-byte aligned: mbarriers, then the tiles the bulk copies write
     uint64_t* ring_bar = (uint64_t*)(base + ((((unsigned char*)(c.dead + 2) - base) + 15) & ~(size_t)15));
     const int stages = b.ring_stages;
@@ -920,7 +928,7 @@ __device__ __forceinline__ void bcp_body(const DbDev& db, const BatchDev& b, int
     // false" literal (FALSE plane all ones, TRUE plane 0), n_lit + 2 / + 3 = the pad variable of
     // gate records (TRUE plane 0, FALSE plane all ones: known, value 0)
     for (int i = lane; i < n_planes; i += 32) c.S[i] = (i == db.n_lit || i == db.n_lit + 3) ? ~(PT)0 : (PT)0;
-    for (int i = lane; i < 3 * iw2; i += 32) c.fill[i] = 0;
+    for (int i = lane; i < 3 * iw2 + lm2; i += 32) c.fill[i] = 0;
     if (lane == 0) {
         for (int s = 0; s < stages; s++) mbar_init(&ring_bar[s], 1);
         mbar_fence_init();
@@ -1097,6 +1105,7 @@ __device__ __forceinline__ void bcp_body(const DbDev& db, const BatchDev& b, int
             // of the literals' complements, are visited as one flattened list each, one record
             // per lane per trip.
             bool stop = false;
+            while (true) {  // levels until the frontier is empty, then the marked long clauses, then again
             while (!stop) {
                 __syncwarp();
                 {
@@ -1184,8 +1193,35 @@ __device__ __forceinline__ void bcp_body(const DbDev& db, const BatchDev& b, int
                             if (i < total) eval_clause(r, db.rec, c, live, pad2);
                         }
                     }
+                    if (db.n_long && have) {
+                        // long clauses that contain the falsified literal: only marked here
+                        const uint32_t nl = myl ^ 1;
+                        for (uint32_t o = locc_off[nl]; o < locc_off[nl + 1]; o++) {
+                            const uint32_t id = locc[o];
+                            atomicOr(&lmark[id >> 5], 1u << (id & 31));
+                        }
+                    }
                     __syncwarp();
                 } while (__any_sync(0xffffffffu, my_bits != 0));
+            }
+                if (stop || !db.n_long) break;
+                // the frontier is empty: every marked long clause is evaluated once (lane L takes the
+                // ids congruent to L); whatever they imply starts the levels again
+                __syncwarp();
+                bool any_marked = false;
+                const PT live_l = valid & ~*(volatile PT*)c.dead;
+                for (int w0 = 0; w0 < lm_words; w0++) {
+                    const uint32_t word = lmark[w0];
+                    if (!word) continue;
+                    any_marked = true;
+                    if ((word >> lane) & 1u) {
+                        const uint4 r = make_uint4(lrec[32 * w0 + lane], 0u, 0u, REC_INDIRECT_D << 16);
+                        eval_clause(r, db.rec, c, live_l, pad2);
+                    }
+                }
+                __syncwarp();
+                for (int w0 = lane; w0 < lm_words; w0 += 32) lmark[w0] = 0;
+                if (!any_marked) break;
             }
             acc.pops += npops;
             __syncwarp();
@@ -1286,6 +1322,8 @@ __device__ __forceinline__ void bcp_body(const DbDev& db, const BatchDev& b, int
                     *reinterpret_cast<typename Plane<PT>::Pair*>(c.S + cd) = z;
                 }
             }
+            if (db.n_long)
+                for (int w0 = lane; w0 < lm_words; w0 += 32) lmark[w0] = 0;
             if (n_touched) {
                 for (int wi = lane; wi < inq_words; wi += 32) {
                     uint32_t bits = c.tset[wi];

@@ -2,6 +2,7 @@
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -187,13 +188,19 @@ static LaunchShape launch_shape_bits(const pdsat_db* db, uint32_t kp_max, int pl
     const int pb = plane_bits / 8;
     const int n_lit = 2 * db->host.n_live, inq_words = (n_lit + 31) / 32;
     // planes + three bitsets (two frontiers, undo set) + the conflict mask (+ alignment slack)
-    const int state = (n_lit + 4) * pb + 3 * ((inq_words + 1) & ~1) * 4 + 2 * pb + 16;
+    const int lm_words = ((int)db->host.long_rec.size() + 31) / 32;
+    const int state = (n_lit + 4) * pb + 3 * ((inq_words + 1) & ~1) * 4 + ((lm_words + 1) & ~1) * 4 + 2 * pb + 16;
     L.warp_bytes = (state + ring + 15) & ~15;
     const int blob = (int)db->host.blob.size();
-    L.blob_in_smem = (blob <= 64 * 1024 && blob + L.warp_bytes <= MAX_SMEM) ? 1 : 0;
-    int wpc = (MAX_SMEM - (L.blob_in_smem ? blob : 0)) / L.warp_bytes;
+    // the index blob is staged in shared memory only where that costs no resident warp (measured:
+    // ODLS 4 warps + staged blob 4.36e8 samples/s, 6 warps + blob through L1/L2 4.80e8; Bivium has
+    // room for both)
     const int cap = plane_bits == 64 ? 16 : 24;  // __launch_bounds__(512) / (768)
-    if (wpc > cap) wpc = cap;
+    const int wpc_without = std::min(cap, MAX_SMEM / L.warp_bytes);
+    const int wpc_with = blob + L.warp_bytes <= MAX_SMEM ? std::min(cap, (MAX_SMEM - blob) / L.warp_bytes) : 0;
+    L.blob_in_smem = (blob <= 64 * 1024 && wpc_with >= 1 && wpc_with == wpc_without) ? 1 : 0;
+    if (const char* e = getenv("PDSAT_BLOB_SMEM")) L.blob_in_smem = (atoi(e) != 0 && wpc_with >= 1) ? 1 : 0;
+    int wpc = L.blob_in_smem ? wpc_with : wpc_without;
     L.wpc = wpc;
     L.smem_bytes = wpc * L.warp_bytes + (L.blob_in_smem ? blob : 0);
     return L;
@@ -243,11 +250,11 @@ static int sync_device_db(pdsat_db* db) {
     size_t nrec = (size_t)h.n_rec;
     CU(cudaMalloc(&db->d_rec, (nrec ? nrec : 1) * sizeof(uint4)));
     CU(cudaMalloc(&db->d_blob, h.blob.size()));
-    CU(cudaMalloc(&db->d_occrec, (h.occ.size() ? h.occ.size() : 1) * sizeof(uint4)));
+    const size_t n_docc = h.occrec.size() / REC_SLOTS;
+    CU(cudaMalloc(&db->d_occrec, (n_docc ? n_docc : 1) * sizeof(uint4)));
     if (nrec) CU(cudaMemcpy(db->d_rec, h.rec.data(), nrec * sizeof(uint4), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(db->d_blob, h.blob.data(), h.blob.size(), cudaMemcpyHostToDevice));
-    if (!h.occ.empty())
-        CU(cudaMemcpy(db->d_occrec, h.occrec.data(), h.occ.size() * sizeof(uint4), cudaMemcpyHostToDevice));
+    if (n_docc) CU(cudaMemcpy(db->d_occrec, h.occrec.data(), n_docc * sizeof(uint4), cudaMemcpyHostToDevice));
     db->dev.rec = db->d_rec;
     db->dev.occrec = db->d_occrec;
     db->dev.blob = db->d_blob;
@@ -255,13 +262,17 @@ static int sync_device_db(pdsat_db* db) {
     db->dev.off_gocc_off = h.blob_gocc_off;
     db->dev.off_gocc = h.blob_gocc;
     db->dev.off_grec = h.blob_grec;
+    db->dev.off_locc_off = h.blob_locc_off;
+    db->dev.off_locc = h.blob_locc;
+    db->dev.off_lrec = h.blob_lrec;
     db->dev.blob_in_smem = L.blob_in_smem;
     db->dev.n_live = h.n_live;
     db->dev.n_lit = n_lit;
     db->dev.n_base_assigned = h.n_base_assigned;
     db->dev.unsat = h.base_ok ? 0 : 1;
     db->dev.n_gates = (int32_t)h.gates.size();
-    db->dev.n_rec = (int32_t)h.n_rec;
+    db->dev.n_rec = (int32_t)n_docc;
+    db->dev.n_long = (int32_t)h.long_rec.size();
     CU(cudaFuncSetAttribute(bcp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM));
     CU(cudaFuncSetAttribute(bcp_kernel_h, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM));
     return PDSAT_OK;
