@@ -466,6 +466,58 @@ def leg_solve(api, torch, dist, rank, world, args):
     return out
 
 
+def leg_odls(api, torch, args):
+    """BASELINE config 5: ODLS order-10 pair CNF (434 440 clauses: the clause database is far
+    larger than shared memory and is read through L2; 10-literal clauses are visited lazily).
+    Predict over 8 cells of square A (80 variables, one random value per cell and sample); the
+    first `check` samples are compared with the reference BCP sample by sample."""
+    from pdsat_b200 import fixtures as fx
+    from oracle import oracle as orc
+    onv, ocl = fx.odls_pair_cnf(10)
+    ooffs, olits = fx.to_csr(ocl)
+    t0 = time.perf_counter()
+    odb = api.ClauseDb(onv, ooffs, olits, device=torch.cuda.current_device())
+    upload_s = time.perf_counter() - t0
+    cells = [(1, 1), (1, 2), (2, 3), (3, 4), (4, 6), (5, 7), (6, 8), (8, 9)]
+    ovars = [fx.odls_var(10, 0, i, j, z) for (i, j) in cells for z in range(10)]
+    n_o = args.odls_samples
+    rng = np.random.default_rng(3)
+    pick = rng.integers(0, 10, size=(n_o, len(cells)))
+    vals = np.zeros((n_o, len(ovars)), dtype=np.uint8)
+    for ci in range(len(cells)):
+        vals[np.arange(n_o), ci * 10 + pick[:, ci]] = 1
+    bo = api.Batch(odb, [api.Point(ovars, n_o, api.MODE_EXPLICIT, explicit_values=vals)], api.OUT_FLAGS | api.OUT_TRAIL)
+    bo.fill()
+    ms = []
+    for it in range(6):
+        bo.propagate()
+        if it:
+            ms.append(bo.last_ms()[1])
+    co = bo.costs()[0]
+    conflict, full = bo.flags(0)
+    trail = bo.trail(0)
+    bo.close()
+    oi = odb.info()
+    n_chk = min(args.odls_check, n_o)
+    O = orc.Oracle(onv, ooffs, olits, cpu_kind())
+    bad = 0
+    t0 = time.perf_counter()
+    for s_ in range(n_chk):
+        r, _ = O.bcp([2 * (v - 1) + (0 if vals[s_][j] else 1) for j, v in enumerate(ovars)], want_assigns=False)
+        if bool(conflict[s_]) != bool(r.conflict) or (not r.conflict and int(trail[s_]) != r.trail_size):
+            bad += 1
+    cpu_s = time.perf_counter() - t0
+    odb.close()
+    med = statistics.median(ms)
+    return {"instance": "ODLS order 10: %d vars, %d clauses (10-literal clauses lazily), %d gates" % (onv, len(ocl), oi.n_gates),
+            "upload_s": upload_s, "samples": n_o, "set_size": len(ovars), "propagate_ms": med,
+            "samples_per_s": n_o / (med * 1e-3), "conflict_frac": co.n_conflict / n_o,
+            "mean_trail_conflict_free": co.sum_trail / max(1, n_o - co.n_conflict),
+            "literal_visits_per_group": co.queue_pops / ((n_o + 63) // 64),
+            "warps_per_cta": oi.warps_per_cta, "index_blob_in_smem": bool(oi.db_in_smem),
+            "parity": {"samples": n_chk, "mismatches": bad, "cpu_bcp_only_samples_per_s_1core": n_chk / cpu_s}}
+
+
 def load_profile_metrics():
     tp = os.path.join(ROOT, "profiles", "bcp_kernel_metrics.json")
     return json.load(open(tp)) if os.path.exists(tp) else {}
@@ -725,6 +777,7 @@ def run_ours(args):
                      "ncu": prof.get("k%d" % k)}
             cascade["k%d" % k] = entry
         extra["cascade"] = cascade
+        extra["odls10_predict"] = leg_odls(api, torch, args)
     # ---------------- configs 3 and 4 at every N (collective legs: all ranks take part)
     if not args.no_extra:
         extra_tabu = leg_tabu(api, torch, dist, db, rank, world, args)
@@ -868,6 +921,8 @@ def main():
     ap.add_argument("--cascade-samples", type=int, default=1_000_000)
     ap.add_argument("--pipeline", type=int, default=8, help="steps in flight in the e2e measurement (1 GPU; 2 when N > 1)")
     ap.add_argument("--tabu-samples", type=int, default=1_000_000, help="samples per point of the tabu-step leg")
+    ap.add_argument("--odls-samples", type=int, default=1_000_000)
+    ap.add_argument("--odls-check", type=int, default=20_000, help="ODLS samples compared with the reference BCP")
     ap.add_argument("--a52-known", type=int, default=32, help="known R1|R2|R3 bits of the A5/2 solve leg (set = 64 - known)")
     ap.add_argument("--solve-check-bits", type=int, default=18, help="log2 size of the slice checked against the CPU")
     ap.add_argument("--reduce", default="auto", choices=["auto", "peer", "nccl"],
