@@ -401,6 +401,13 @@ def leg_solve(api, torch, dist, rank, world, args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    times = []
+    for rep in range(3):  # the first repetition also pays the allocations of the level batches
+        barrier()
+        t0 = time.perf_counter()
+        surv, ism, st = db.enumerate(dset, n_fixed_top=top, fixed_top_value=rank, max_survivors=1 << 12)
+        barrier()
+        times.append(time.perf_counter() - t0)
     barrier()
     t0 = time.perf_counter()
     surv, ism, st = db.enumerate(dset, n_fixed_top=top, fixed_top_value=rank, max_survivors=1 << 12)
@@ -422,7 +429,8 @@ def leg_solve(api, torch, dist, rank, world, args):
     tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    dt = float(tt.item())
+    times.append(float(tt.item()))
+    dt = statistics.median(times)
     out = None
     if rank == 0:
         gathered = sorted(int(x) for h in all_hits for x in h.tolist() if x >= 0)
@@ -448,7 +456,7 @@ def leg_solve(api, torch, dist, rank, world, args):
                            (nv, len(cl), 114, args.a52_known),
                "set_size": k, "assignments": 1 << k, "ranks": world, "upload_s": upload_s,
                "live_vars": info.n_live_vars, "gates": info.n_gates, "warps_per_cta": info.warps_per_cta,
-               "seconds": dt, "assignments_per_s": (1 << k) / dt,
+               "seconds": dt, "seconds_all": times, "assignments_per_s": (1 << k) / dt,
                "found_flag": int(found.item()), "hit_indices": gathered, "secret_index": idx,
                "secret_found": idx in gathered,
                "conflicts": n_conf, "models": n_mod, "undecided": n_und,
