@@ -474,6 +474,37 @@ int main(int argc, char** argv) {
                cnf.output_variables, cnf.known_bits, cnf.var_set.size());
         return 0;
     }
+    if (argc >= 8 && std::string(argv[1]) == "--search-selftest") {
+        // the search driver on a synthetic objective (no GPU): pd-sat-b200 --search-selftest n_vars deep ts seed steps init_size
+        // predict(set) = 1000 + sum over v in set of ((37 v) mod 11 - 4) + 3 * (|set| mod 5)  (integers: exact everywhere)
+        SearchParams P;
+        const int n = atoi(argv[2]);
+        for (int v = 1; v <= n; v++) P.full_vars.push_back(v);
+        P.deep_predict = atoi(argv[3]);
+        P.ts_strategy = atoi(argv[4]);
+        P.seed = (uint32_t)strtoul(argv[5], 0, 10);
+        P.max_steps = atoi(argv[6]);
+        P.write_files = false;
+        P.min_temperature = 0.5;
+        SearchDriver S(P, [&](std::vector<PointEval>& pts) {
+            for (auto& q : pts) {
+                long long p = 1000 + 3 * (long long)(q.set.size() % 5);
+                for (int32_t v : q.set) p += (37 * v) % 11 - 4;
+                q.est.predict = (long double)p;
+                q.est.sum = (double)p;
+                q.cost.n = 1;
+            }
+            return true;
+        });
+        std::vector<int32_t> init;
+        for (int v = 1; v <= atoi(argv[7]); v++) init.push_back(v);
+        if (!S.run(init)) return 1;
+        for (size_t i = 0; i < S.centre_history.size(); i++) std::cout << "centre " << i << " : " << set_to_string(S.centre_history[i]) << std::endl;
+        std::cout << "best_set " << set_to_string(S.best_set) << std::endl;
+        std::cout << "best_predict " << (double)S.best_predict << std::endl;
+        std::cout << "records " << S.record_count << std::endl;
+        return 0;
+    }
     Flags f;
     if (!parse_flags(argc, argv, f)) {
         std::cerr << "usage: pd-sat-b200 <input_cnf> [split_var_count] [-cnf_in_set=N] [-deep_predict=D] [-proc=P] [-core=N]\n"

@@ -63,6 +63,37 @@ def _predict_rows(path):
     return rows
 
 
+@pytest.mark.parametrize("deep,ts", [(6, 0), (5, 0), (6, 4), (6, 2), (3, 0)])
+def test_search_driver_selftest_matches_python_mirror(deep, ts, cli):
+    """The C++ search driver (host/search.hpp) on a synthetic integer objective, no GPU: every
+    step's centre, the records and the final set equal the Python mirror's (tests/search_mirror.py)
+    - tabu lists, L2 jumps with the mt19937 draws, annealing acceptance, swap / window strategies."""
+    from oracle import oracle as orc
+    from search_mirror import Mirror
+    orc.build()
+    n, seed, steps, init = 24, 9, 25, 12
+
+    def evaluate(sets):
+        return [(float(1000 + 3 * (len(s_) % 5) + sum((37 * v) % 11 - 4 for v in s_)), 0) for s_ in sets]
+
+    def draws(sd):
+        first = 0
+        while True:
+            for x in orc.mt19937_draws(sd, first, 256):
+                yield int(x)
+            first += 256
+
+    out = subprocess.check_output([cli, "--search-selftest", str(n), str(deep), str(ts), str(seed), str(steps), str(init)]).decode()
+    centres = [[int(x) for x in l.split(":")[1].split()] for l in out.splitlines() if l.startswith("centre ")]
+    vals = dict(l.split(" ", 1) for l in out.splitlines() if not l.startswith("centre "))
+    M = Mirror(list(range(1, n + 1)), evaluate, deep_predict=deep, ts_strategy=ts, seed=seed, max_steps=steps, draws=draws,
+               min_temperature=0.5).run(list(range(1, init + 1)))
+    assert centres == M.centres
+    assert [int(x) for x in vals["best_set"].split()] == M.best_set
+    assert float(vals["best_predict"]) == M.best and int(vals["records"]) == len(M.records)
+    assert len(centres) >= 3
+
+
 @pytest.mark.gpu
 def test_cli_predict_matches_python_mirror(cli, tmp_path):
     import bench
