@@ -59,8 +59,15 @@ struct PointDev {
     uint64_t block_off;       // ENUM_BLOCKS: first prefix of this point in block_prefix
     uint32_t block_bits;
     uint32_t pad_;
+    uint64_t run_start;       // first global RUN of this point
+    uint32_t tile;            // groups per run: 1, or BatchDev::tile_groups for a streaming point
+    uint32_t pad2_;
 };
 static constexpr uint32_t POINT_HAS_FIXED = 1u;  // some set variable is assigned at level 0
+// BCP cannot start in this point (no candidate record, no level-0-fixed set variable, not every live
+// variable assumed, no assignment output; or the database itself is refuted): the host decides,
+// gives the point runs of several groups and the kernel streams through them
+static constexpr uint32_t POINT_STREAMING = 2u;
 
 static constexpr uint32_t SETCODE_FIXED = 0x80000000u;  // set var already assigned at level 0; bit0 = its lbool
 
@@ -109,12 +116,25 @@ struct BatchDev {
     uint64_t* model_sample;
     int32_t max_models;
     int32_t model_words;
-    // per-warp ring of assumption-word tiles (bulk async copies): stages x stage_bytes
+    // per-warp ring of assumption-word tiles (bulk async copies): stages x stage_bytes; a tile
+    // holds the words of one run = PointDev::tile consecutive groups of a point (one bulk copy)
     int32_t ring_stages;
     int32_t ring_stage_bytes;
+    int32_t tile_groups;
+    uint64_t n_runs;
     // fused cost all-reduce over NVLink peer memory (0 ranks = off, see PeerDev)
     PeerDev peer;
 };
+
+__device__ __forceinline__ int find_point_run(const PointDev* pts, int n, uint64_t r) {
+    int lo = 0, hi = n - 1;
+    while (lo < hi) {
+        int mid = (lo + hi + 1) >> 1;
+        if (pts[mid].run_start <= r) lo = mid;
+        else hi = mid - 1;
+    }
+    return lo;
+}
 
 __device__ __forceinline__ int find_point(const PointDev* pts, int n, uint64_t g) {
     int lo = 0, hi = n - 1;
@@ -774,24 +794,21 @@ __device__ __forceinline__ uint64_t warp_sum64(uint64_t v) {
 
 static constexpr int MAX_COUNT_BITS = 15;
 
-struct WarpAcc {
-    uint64_t n, n_conflict, n_full, sum, sumsq, n_impl, pops, touched;
-    int point;
-};
+// Per-warp accumulators of the current point: 8 x u64 in the warp's shared memory (lane 0 adds;
+// sixteen registers less in the propagation loop), flushed with <= 8 atomicAdds per point change.
+enum { ACC_N = 0, ACC_CONFLICT, ACC_FULL, ACC_SUM, ACC_SUMSQ, ACC_IMPL, ACC_POPS, ACC_TOUCHED };
 
-__device__ __forceinline__ void flush_acc(WarpAcc& a, unsigned long long* cost, int lane) {
-    if (a.point >= 0 && lane == 0 && a.n) {
-        unsigned long long* c = cost + (size_t)a.point * 8;
-        atomicAdd(&c[0], (unsigned long long)a.n);
-        if (a.n_conflict) atomicAdd(&c[1], (unsigned long long)a.n_conflict);
-        if (a.n_full) atomicAdd(&c[2], (unsigned long long)a.n_full);
-        atomicAdd(&c[3], (unsigned long long)a.sum);
-        atomicAdd(&c[4], (unsigned long long)a.sumsq);
-        if (a.n_impl) atomicAdd(&c[5], (unsigned long long)a.n_impl);
-        if (a.pops) atomicAdd(&c[6], (unsigned long long)a.pops);
-        if (a.touched) atomicAdd(&c[7], (unsigned long long)a.touched);
+__device__ __forceinline__ void flush_acc(uint64_t* a, int point, unsigned long long* cost, int lane) {
+    if (lane == 0) {
+        if (point >= 0 && a[ACC_N]) {
+            unsigned long long* c = cost + (size_t)point * 8;
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+                if (a[i]) atomicAdd(&c[i], (unsigned long long)a[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; i++) a[i] = 0;
     }
-    a.n = a.n_conflict = a.n_full = a.sum = a.sumsq = a.n_impl = a.pops = a.touched = 0;
 }
 
 // owner of flattened item i among the lanes' lists: the smallest q with cum[q] > i (cum =
@@ -919,8 +936,9 @@ __device__ __forceinline__ void bcp_body(const DbDev& db, const BatchDev& b, int
     const int lm_words = (db.n_long + 31) >> 5;
     const int lm2 = (lm_words + 1) & ~1;
     c.dead = (PT*)(lmark + lm2);
-    // 16-byte aligned: mbarriers, then the tiles the bulk copies write
-    uint64_t* ring_bar = (uint64_t*)(base + ((((unsigned char*)(c.dead + 2) - base) + 15) & ~(size_t)15));
+    // 16-byte aligned: the point accumulators, mbarriers, then the tiles the bulk copies write
+    uint64_t* accs = (uint64_t*)(base + ((((unsigned char*)(c.dead + 2) - base) + 15) & ~(size_t)15));
+    uint64_t* ring_bar = accs + 8;
     const int stages = b.ring_stages;
     unsigned char* ring = (unsigned char*)(ring_bar + ((stages + 1) & ~1));
 
@@ -936,38 +954,46 @@ __device__ __forceinline__ void bcp_body(const DbDev& db, const BatchDev& b, int
     __syncwarp();
 
     const uint32_t pad2 = (uint32_t)db.n_lit | ((uint32_t)db.n_lit << 16);  // two pad slots
-    WarpAcc acc;
-    acc.n = acc.n_conflict = acc.n_full = acc.sum = acc.sumsq = acc.n_impl = acc.pops = acc.touched = 0;
-    acc.point = -1;
+    if (lane < 8) accs[lane] = 0;
+    __syncwarp();
 
+    // The unit of work of a warp is a RUN: tile_groups consecutive groups of one point, whose
+    // words are contiguous in HBM and arrive with ONE bulk copy (runs never straddle points).
     const uint64_t stride = (uint64_t)gridDim.x * wpc;
-    const uint64_t g_first = (uint64_t)blockIdx.x * wpc + warp;
+    const uint64_t r_first = (uint64_t)blockIdx.x * wpc + warp;
 
-    // ---- producer side of the words ring (lane 0): group pf_g goes to stage pf_stage.  Inside a
-    // point the source pointer just advances by the warp's group stride.
+    // ---- producer side of the words ring (lane 0): run pf_r goes to stage pf_stage
     const uint32_t ring_s = smem_u32(ring), bar_s = smem_u32(ring_bar);
     const uint32_t stage_bytes = (uint32_t)b.ring_stage_bytes;
-    uint64_t pf_g = g_first;
+    uint64_t pf_r = r_first;
     uint32_t pf_stage = 0;
-    uint64_t pf_end = 0;
-    const uint64_t* pf_ptr = nullptr;
-    uint32_t pf_bytes = 0;
-    uint64_t pf_step = 0;
+    uint64_t pf_run_end = 0;
+    const uint64_t* pf_ptr = nullptr;  // source of the next run of this warp inside the current point
+    uint64_t pf_step = 0;              // words between two runs of this warp
+    int64_t pf_left = 0, pf_gstep = 0; // groups from the next run's first group to the end of the point
+    uint32_t pf_T = 1, pf_gbytes = 0;
     auto prefetch_one = [&]() {
-        if (pf_g < b.n_groups) {
-            if (pf_g >= pf_end) {
-                const int pp = find_point(b.points, b.n_points, pf_g);
+        if (pf_r < b.n_runs) {
+            if (pf_r >= pf_run_end) {
+                const int pp = find_point_run(b.points, b.n_points, pf_r);
                 const PointDev* pt = &b.points[pp];
-                pf_end = pp + 1 < b.n_points ? b.points[pp + 1].group_start : b.n_groups;
-                pf_ptr = b.words + pt->word_off + (pf_g - pt->group_start) * pt->kp;
-                pf_bytes = pt->kp * 8u;
-                pf_step = stride * pt->kp;
+                pf_run_end = pp + 1 < b.n_points ? b.points[pp + 1].run_start : b.n_runs;
+                pf_T = pt->tile;
+                const uint64_t groups = (pp + 1 < b.n_points ? b.points[pp + 1].group_start : b.n_groups) - pt->group_start;
+                const uint64_t g_rel = (pf_r - pt->run_start) * pf_T;  // first group of the run inside its point
+                pf_ptr = b.words + pt->word_off + g_rel * pt->kp;
+                pf_left = (int64_t)(groups - g_rel);
+                pf_gstep = (int64_t)(stride * pf_T);
+                pf_step = stride * pf_T * pt->kp;
+                pf_gbytes = pt->kp * 8u;
             }
-            mbar_expect_tx_s(bar_s + pf_stage * 8u, pf_bytes);
-            bulk_g2s_s(ring_s + pf_stage * stage_bytes, pf_ptr, pf_bytes, bar_s + pf_stage * 8u);
+            const uint32_t bytes = (pf_left >= (int64_t)pf_T ? pf_T : (uint32_t)pf_left) * pf_gbytes;
+            mbar_expect_tx_s(bar_s + pf_stage * 8u, bytes);
+            bulk_g2s_s(ring_s + pf_stage * stage_bytes, pf_ptr, bytes, bar_s + pf_stage * 8u);
             pf_ptr += pf_step;
+            pf_left -= pf_gstep;
         }
-        pf_g += stride;
+        pf_r += stride;
         pf_stage = pf_stage + 1 == (uint32_t)stages ? 0 : pf_stage + 1;
     };
     if (lane == 0)
@@ -979,17 +1005,19 @@ __device__ __forceinline__ void bcp_body(const DbDev& db, const BatchDev& b, int
     }
 
     // current point, cached in registers (a warp usually stays inside one point for many groups)
-    int p = -1;
-    uint64_t P_start = 0, P_end = 0, P_n_samples = 0;
+    int p = -1, p_prev = -1;
+    uint64_t P_start = 0, P_end = 0, P_n_samples = 0, P_run_start = 0, P_run_end = 0;
     uint32_t k = 0, P_var_off = 0, P_n_assumed = 0, P_cand_off = 0, P_cand_cnt = 0, P_code0 = 0, P_flags = 0;
     int stage = 0;
     uint32_t phase = 0;
-    for (uint64_t g = g_first; g < b.n_groups; g += stride) {
-        if (p < 0 || g >= P_end) {
-            p = find_point(b.points, b.n_points, g);
+    for (uint64_t run = r_first; run < b.n_runs; run += stride) {
+        if (p < 0 || run >= P_run_end) {
+            p = find_point_run(b.points, b.n_points, run);
             const PointDev* pt = &b.points[p];
             P_start = pt->group_start;
             P_end = p + 1 < b.n_points ? b.points[p + 1].group_start : b.n_groups;
+            P_run_start = pt->run_start;
+            P_run_end = p + 1 < b.n_points ? b.points[p + 1].run_start : b.n_runs;
             P_n_samples = pt->n_samples;
             k = pt->k;
             P_var_off = pt->var_off;
@@ -998,22 +1026,22 @@ __device__ __forceinline__ void bcp_body(const DbDev& db, const BatchDev& b, int
             P_cand_cnt = pt->cand_cnt;
             P_flags = pt->flags;
             P_code0 = lane < (int)k ? b.setcode[P_var_off + lane] : 0u;
-            flush_acc(acc, b.cost, lane);
-            acc.point = p;
+            flush_acc(accs, p_prev, b.cost, lane);
+            p_prev = p;
         }
         // BCP can only start from a candidate record or a contradicted level-0 value (a set that
-        // covers every live variable also goes the long way: its samples are models)
-        const bool active = !db.unsat && (P_cand_cnt != 0 || (P_flags & POINT_HAS_FIXED) != 0 || b.assign != nullptr ||
-                                          P_n_assumed == (uint32_t)db.n_live);
-        if (!active) {
+        // covers every live variable also goes the long way: its samples are models); the host
+        // marks the points where it cannot
+        if (P_flags & POINT_STREAMING) {
             // ---- streaming path: nothing can be implied or falsified in the groups of this
             // point.  Each tile is released as soon as it has landed; every sample has the trail
             // level-0 + assumptions (or is a conflict if the database itself is refuted).  The
-            // loop runs over all groups of this warp inside the point.
+            // loop runs over all runs of this warp inside the point.
             const uint32_t tr = db.n_base_assigned + P_n_assumed;
             const uint64_t g_last = P_end - 1;  // the only group of the point that can be ragged
             const uint32_t n_tail = (uint32_t)(P_n_samples - (g_last - P_start) * 64);
             const bool want_out = b.conflict_bits != nullptr || b.trail != nullptr;
+            const uint32_t T = b.points[p].tile;
             uint32_t cnt = 0;
             while (true) {
                 mbar_wait_s(bar_s + (uint32_t)stage * 8u, phase);  // the tile has landed (and is not needed)
@@ -1021,33 +1049,42 @@ __device__ __forceinline__ void bcp_body(const DbDev& db, const BatchDev& b, int
                 if (lane == 0) prefetch_one();
                 stage = stage + 1 == stages ? 0 : stage + 1;
                 phase ^= (stage == 0);
-                const uint32_t nv = g == g_last ? n_tail : 64u;
-                cnt += nv;
+                const uint64_t g0 = P_start + (run - P_run_start) * T;
+                const uint32_t ng = (uint32_t)min((uint64_t)T, P_end - g0);
+                cnt += g0 + ng - 1 == g_last ? (ng - 1) * 64u + n_tail : ng * 64u;
                 if (want_out) {
-                    const uint64_t vm = nv >= 64 ? ~0ull : ((1ull << nv) - 1);
-                    if (b.conflict_bits && lane == 0) {
-                        b.conflict_bits[g] = db.unsat ? vm : 0ull;
-                        b.full_bits[g] = 0ull;
-                    }
-                    if (b.trail) {
-                        b.trail[g * 64 + lane] = (!db.unsat && ((vm >> lane) & 1ull)) ? tr : 0u;
-                        b.trail[g * 64 + 32 + lane] = (!db.unsat && ((vm >> (lane + 32)) & 1ull)) ? tr : 0u;
+                    for (uint32_t gg = 0; gg < ng; gg++) {
+                        const uint64_t g = g0 + gg;
+                        const uint32_t nv = g == g_last ? n_tail : 64u;
+                        const uint64_t vm = nv >= 64 ? ~0ull : ((1ull << nv) - 1);
+                        if (b.conflict_bits && lane == 0) {
+                            b.conflict_bits[g] = db.unsat ? vm : 0ull;
+                            b.full_bits[g] = 0ull;
+                        }
+                        if (b.trail) {
+                            b.trail[g * 64 + lane] = (!db.unsat && ((vm >> lane) & 1ull)) ? tr : 0u;
+                            b.trail[g * 64 + 32 + lane] = (!db.unsat && ((vm >> (lane + 32)) & 1ull)) ? tr : 0u;
+                        }
                     }
                 }
-                if (g + stride >= P_end) break;
-                g += stride;
+                if (run + stride >= P_run_end) break;
+                run += stride;
             }
-            acc.n += cnt;
-            if (db.unsat) {
-                acc.n_conflict += cnt;
-            } else {
-                acc.sum += (uint64_t)cnt * tr;
-                acc.sumsq += (uint64_t)cnt * tr * tr;
+            if (lane == 0) {
+                accs[ACC_N] += cnt;
+                if (db.unsat) {
+                    accs[ACC_CONFLICT] += cnt;
+                } else {
+                    accs[ACC_SUM] += (uint64_t)cnt * tr;
+                    accs[ACC_SUMSQ] += (uint64_t)cnt * tr * tr;
+                }
             }
             continue;
         }
 
-        const uint64_t gi = g - P_start;
+        // a point in which BCP can start has runs of one group
+        const uint64_t gi = run - P_run_start;
+        const uint64_t g = P_start + gi;
         const uint64_t s0 = gi * 64;
         const uint64_t left = P_n_samples - s0;
         const uint64_t valid64 = left >= 64 ? ~0ull : ((1ull << left) - 1);
@@ -1080,7 +1117,7 @@ __device__ __forceinline__ void bcp_body(const DbDev& db, const BatchDev& b, int
             }
             __syncwarp();
             if (half == HALVES - 1 || !(PT)(valid64 >> (W * (HALVES - 1)))) {
-                // the stage is free again: request the tile `stages` groups ahead
+                // the stage is free again: request the tile `stages` runs ahead
                 if (lane == 0) prefetch_one();
                 stage = stage + 1 == stages ? 0 : stage + 1;
                 phase ^= (stage == 0);
@@ -1223,7 +1260,7 @@ __device__ __forceinline__ void bcp_body(const DbDev& db, const BatchDev& b, int
                 for (int w0 = lane; w0 < lm_words; w0 += 32) lmark[w0] = 0;
                 if (!any_marked) break;
             }
-            acc.pops += npops;
+            if (lane == 0) accs[ACC_POPS] += npops;
             __syncwarp();
 
             // ---- (4) per-sample results
@@ -1240,7 +1277,7 @@ __device__ __forceinline__ void bcp_body(const DbDev& db, const BatchDev& b, int
                 }
                 n_touched = __reduce_add_sync(0xffffffffu, lcnt);
             }
-            acc.touched += n_touched;
+            if (lane == 0) accs[ACC_TOUCHED] += n_touched;
             uint32_t cnt0, cnt1 = 0;  // assigned live variables of samples lane, lane+32
             if (n_touched == 0 || okm == 0) {  // counts only matter for conflict-free samples
                 cnt0 = cnt1 = P_n_assumed;
@@ -1262,21 +1299,29 @@ __device__ __forceinline__ void bcp_body(const DbDev& db, const BatchDev& b, int
             const uint32_t t0 = db.n_base_assigned + cnt0, t1 = db.n_base_assigned + cnt1;
             if (n_touched == 0 || okm == 0) {
                 const uint64_t nok = Plane<PT>::popc(okm);
-                acc.sum += nok * t0;
-                acc.sumsq += nok * (uint64_t)t0 * t0;
+                if (lane == 0) {
+                    accs[ACC_SUM] += nok * t0;
+                    accs[ACC_SUMSQ] += nok * (uint64_t)t0 * t0;
+                }
             } else {
                 // 64-bit throughout: trail can reach n_vars, its square summed over 64 samples
                 // does not fit 32 bits from trail = 8192 on
                 const uint64_t lsum = (ok0 ? (uint64_t)t0 : 0ull) + (ok1 ? (uint64_t)t1 : 0ull);
                 const uint64_t lsq = (ok0 ? (uint64_t)t0 * t0 : 0ull) + (ok1 ? (uint64_t)t1 * t1 : 0ull);
                 const uint32_t limp = (ok0 && cnt0 > P_n_assumed ? 1 : 0) + (ok1 && cnt1 > P_n_assumed ? 1 : 0);
-                acc.sum += warp_sum64(lsum);
-                acc.sumsq += warp_sum64(lsq);
-                acc.n_impl += __reduce_add_sync(0xffffffffu, limp);
+                const uint64_t ws = warp_sum64(lsum), wq = warp_sum64(lsq);
+                const uint32_t wi_ = __reduce_add_sync(0xffffffffu, limp);
+                if (lane == 0) {
+                    accs[ACC_SUM] += ws;
+                    accs[ACC_SUMSQ] += wq;
+                    accs[ACC_IMPL] += wi_;
+                }
             }
-            acc.n += Plane<PT>::popc(valid);
-            acc.n_conflict += Plane<PT>::popc(dead);
-            acc.n_full += __popcll(fullm);
+            if (lane == 0) {
+                accs[ACC_N] += Plane<PT>::popc(valid);
+                accs[ACC_CONFLICT] += Plane<PT>::popc(dead);
+                accs[ACC_FULL] += __popcll(fullm);
+            }
             dead64 |= (uint64_t)dead << (W * half);
             full64 |= fullm << (W * half);
 
@@ -1344,7 +1389,7 @@ __device__ __forceinline__ void bcp_body(const DbDev& db, const BatchDev& b, int
             b.full_bits[g] = full64;
         }
     }
-    flush_acc(acc, b.cost, lane);
+    flush_acc(accs, p_prev, b.cost, lane);
 
     if (b.peer.n_ranks > 0) {
         // the last CTA of this rank exchanges the rank's sums with every peer (see PeerDev)

@@ -32,6 +32,7 @@ static int fail(int code, const std::string& msg) {
 
 struct LaunchShape {
     int stages = 0, stage_bytes = 0, warp_bytes = 0, wpc = 0, smem_bytes = 0, blob_in_smem = 0;
+    int tile_groups = 1;  // groups per run = per bulk copy
     int plane_bits = 64;  // 64: bcp_kernel, 32: bcp_kernel_h (two half passes per group)
 };
 
@@ -68,7 +69,7 @@ struct HostPoint {
     std::vector<uint32_t> setcode;
     int32_t mode = 0;
     uint64_t seed = 0, first_sample = 0, n_samples = 0, first_draw = 0;
-    uint32_t kp = 0, flags = 0, block_bits = 0;
+    uint32_t kp = 0, flags = 0, block_bits = 0, tile = 1;
     uint64_t block_off = 0, block_cap = 0;  // ENUM_BLOCKS: offset / capacity in the prefix buffer
     uint64_t n_groups = 0, group_start = 0, word_off = 0, stream_off = 0, stream_skip = 0, stream_words = 0;
     uint64_t mt_first_round = 0, mt_rounds = 0;
@@ -176,20 +177,31 @@ static int count_bits_for(int n) {
 static constexpr int MAX_SMEM = 227 * 1024 - 128;  // the kernel also has a few bytes of static shared memory
 
 // launch shape of the BCP kernel for a batch whose largest set has kp_max (even) words per group
-static LaunchShape launch_shape_bits(const pdsat_db* db, uint32_t kp_max, int plane_bits) {
+// groups per run (= per bulk copy) of a streaming point with kp words per group: ~2 KB per copy
+// (the producer lane's issue work is per copy)
+static uint32_t tile_groups_for(uint32_t kp) {
+    if (const char* e = getenv("PDSAT_TILE_GROUPS")) return atoi(e) > 0 ? (uint32_t)atoi(e) : 1u;
+    const uint32_t tg = 2048u / (kp * 8u ? kp * 8u : 16u);
+    return tg < 1 ? 1 : (tg > 8 ? 8 : tg);
+}
+
+// stage_bytes = the largest tile of the batch (a point in which BCP can start has tiles of one
+// group, a streaming point of tile_groups_for(kp) groups)
+static LaunchShape launch_shape_bits(const pdsat_db* db, uint32_t stage_bytes, int plane_bits) {
     LaunchShape L;
     L.plane_bits = plane_bits;
-    L.stage_bytes = (int)kp_max * 8;
-    // ~2.25 KB of tiles in flight per warp (x 12..16 warps x 148 SMs covers the HBM latency x
-    // bandwidth product for the small sets); at least double buffering for the large ones
-    int st = 2304 / (L.stage_bytes > 0 ? L.stage_bytes : 16);
-    L.stages = st < 2 ? 2 : (st > 12 ? 12 : st);
+    // 3 KB of tiles in flight per warp (x 12..16 warps x 148 SMs covers the HBM latency x
+    // bandwidth product); at least double buffering for the large sets
+    L.stage_bytes = (int)stage_bytes;
+    int st = 3072 / (L.stage_bytes > 0 ? L.stage_bytes : 16);
+    L.stages = st < 2 ? 2 : (st > 8 ? 8 : st);
     const int ring = ((L.stages + 1) & ~1) * 8 + L.stages * L.stage_bytes;
     const int pb = plane_bits / 8;
     const int n_lit = 2 * db->host.n_live, inq_words = (n_lit + 31) / 32;
     // planes + three bitsets (two frontiers, undo set) + the conflict mask (+ alignment slack)
     const int lm_words = ((int)db->host.long_rec.size() + 31) / 32;
-    const int state = (n_lit + 4) * pb + 3 * ((inq_words + 1) & ~1) * 4 + ((lm_words + 1) & ~1) * 4 + 2 * pb + 16;
+    // planes, 3 frontier / undo bitsets, long-clause marks, conflict mask, alignment, 8 point accumulators
+    const int state = (n_lit + 4) * pb + 3 * ((inq_words + 1) & ~1) * 4 + ((lm_words + 1) & ~1) * 4 + 2 * pb + 16 + 64;
     L.warp_bytes = (state + ring + 15) & ~15;
     const int blob = (int)db->host.blob.size();
     // the index blob is staged in shared memory only where that costs no resident warp (measured:
@@ -212,13 +224,13 @@ static LaunchShape launch_shape_bits(const pdsat_db* db, uint32_t kp_max, int pl
 // faster with half planes; ODLS (5 -> 11 warps) and Bivium (16 -> 24) slower, because a literal
 // implied in both halves is visited twice (ODLS: 1.97x the literal visits).
 // PDSAT_PLANE_BITS=32|64 overrides (experiments, before/after profiles).
-static LaunchShape launch_shape(const pdsat_db* db, uint32_t kp_max) {
+static LaunchShape launch_shape(const pdsat_db* db, uint32_t stage_bytes) {
     const char* e = getenv("PDSAT_PLANE_BITS");
     const int forced = e ? atoi(e) : 0;
-    if (forced == 32 || forced == 64) return launch_shape_bits(db, kp_max, forced);
-    const LaunchShape L64 = launch_shape_bits(db, kp_max, 64);
+    if (forced == 32 || forced == 64) return launch_shape_bits(db, stage_bytes, forced);
+    const LaunchShape L64 = launch_shape_bits(db, stage_bytes, 64);
     if (L64.wpc >= 4) return L64;
-    const LaunchShape L32 = launch_shape_bits(db, kp_max, 32);
+    const LaunchShape L32 = launch_shape_bits(db, stage_bytes, 32);
     return L32.wpc > L64.wpc ? L32 : L64;
 }
 
@@ -243,7 +255,7 @@ static int sync_device_db(pdsat_db* db) {
     // shape for a small set, reported by pdsat_db_get_info; wpc == 0: the planes of one
     // 64-sample group do not fit in shared memory with the current level-0 assignment;
     // evaluation is refused (PDSAT_ERR_LIMIT) until fixed assumptions shrink the live set
-    const LaunchShape L = launch_shape(db, 32);
+    const LaunchShape L = launch_shape(db, 32 * 8);
     db->warps_per_cta = L.wpc;
     db->smem_bytes = L.smem_bytes;
     db->grid = db->sm_count;
@@ -593,7 +605,17 @@ int pdsat_batch_create(pdsat_db* db, int32_t n_points, const pdsat_point* points
     }
     b->n_groups = groups;
     b->n_words = words;
-    b->shape = launch_shape(db, kp_max);
+    // points in which BCP cannot start are streamed through in runs of several groups
+    uint32_t stage_bytes = 16;
+    for (auto& hp : b->pts) {
+        const bool can_start = h.base_ok && (!hp.cand.empty() || !hp.gcand.empty() || (hp.flags & POINT_HAS_FIXED) ||
+                                             (out_flags & PDSAT_OUT_ASSIGN) || hp.n_assumed_live == (uint32_t)h.n_live);
+        if (!can_start) hp.flags |= POINT_STREAMING;
+        hp.tile = can_start ? 1u : tile_groups_for(hp.kp);
+        stage_bytes = std::max(stage_bytes, hp.tile * hp.kp * 8u);
+    }
+    (void)kp_max;
+    b->shape = launch_shape(db, stage_bytes);
     if (b->shape.wpc < 1) {
         pdsat_batch_destroy(b);
         return fail(PDSAT_ERR_LIMIT, "assignment state + word tiles of one sample group exceed shared memory");
@@ -695,6 +717,8 @@ int pdsat_batch_create(pdsat_db* db, int32_t n_points, const pdsat_point* points
             pd.block_off = hp.block_off;
             pd.block_bits = hp.block_bits;
             pd.pad_ = 0;
+            pd.tile = hp.tile;
+            pd.pad2_ = 0;
             off += pd.k;
             codes.insert(codes.end(), hp.setcode.begin(), hp.setcode.end());
             if (pd.cand_cnt) {  // gates first, then clauses: neighbouring lanes take the same path
@@ -772,6 +796,13 @@ int pdsat_batch_fill(pdsat_batch* b) {
     staging_wait(b);  // the previous fill may still be reading the pinned staging buffers
     cudaStream_t st = db->stream;
     CU(cudaEventRecord(b->ev[0], st));
+    {
+        uint64_t runs = 0;  // first run of every point (a run = tile_groups consecutive groups, one bulk copy)
+        for (size_t p = 0; p < b->pts.size(); p++) {
+            b->h_points[p].run_start = runs;
+            runs += (b->pts[p].n_groups + b->pts[p].tile - 1) / b->pts[p].tile;
+        }
+    }
     CU(cudaMemcpyAsync(b->d_points, b->h_points, sizeof(PointDev) * b->pts.size(), cudaMemcpyHostToDevice, st));
     int64_t h2d = (int64_t)(sizeof(PointDev) * b->pts.size());
     if (b->n_mt_segs) {
@@ -944,9 +975,15 @@ int pdsat_batch_propagate(pdsat_batch* b) {
     const LaunchShape& L = b->shape;
     bd.ring_stages = L.stages;
     bd.ring_stage_bytes = L.stage_bytes;
+    bd.tile_groups = 0;  // per point (PointDev::tile)
+    {   // runs: tile_groups consecutive groups of a point (run_start of every point went up with the fill)
+        uint64_t runs = 0;
+        for (size_t p = 0; p < b->pts.size(); p++) runs += (b->pts[p].n_groups + b->pts[p].tile - 1) / b->pts[p].tile;
+        bd.n_runs = runs;
+    }
     DbDev dev = db->dev;
     dev.blob_in_smem = L.blob_in_smem;
-    uint64_t ctas_needed = (b->n_groups + L.wpc - 1) / L.wpc;
+    uint64_t ctas_needed = (bd.n_runs + L.wpc - 1) / L.wpc;
     int grid = (int)(ctas_needed < (uint64_t)db->grid ? ctas_needed : (uint64_t)db->grid);
     if (grid < 1) grid = 1;
     const int n_cost_words = PDSAT_COST_WORDS * (int)b->pts.size();
