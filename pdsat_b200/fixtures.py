@@ -2,7 +2,8 @@
 
 Nothing here is copied from the reference tree: the CNFs are *generated* from the
 cipher / Latin-square definitions and, where the reference ships the same instance,
-checked against it in tests (`tests/test_fixtures.py`, only when /root/reference exists).
+checked against it in tests (`tests/test_host.py::test_bivium_template_equals_reference`, only when
+/root/reference exists).
 
 * `bivium_template()`     reproduces src_common/bivium_template.cnf line for line
                           (777 vars, 12 800 clauses).

@@ -425,3 +425,36 @@ def test_config0_predict_estimate_matches_reference_path(k, bivium, golden, orac
     assert abs(float((res.predict - np.longdouble(ref_pred)) / np.longdouble(ref_pred))) <= 1e-12
     assert abs(pr.sample_variance(res.cost) - (oracle_mod.sample_variance(cost) if cost.std() > 0 else 0.0)) <= \
         1e-12 * max(1.0, oracle_mod.sample_variance(cost))
+
+
+@pytest.mark.parametrize("k", [86, 88, 100])
+def test_estimates_on_sets_with_conflicts(k, bivium, golden, oracle_mod, cuda_lib):
+    """What the two estimates are on sets where BCP hits conflicts (round 1 only checked
+    conflict-free sets).  "prep": getCurPredictTime (src_mpi/mpi_predicter.cpp:1846-1901) with
+    solved = samples BCP decides - reference arithmetic on the reference's own per-sample prep flags.
+    "bcp_trail": GetPredict (:1976-1996) on the costs  trail(sample) for conflict-free samples, 0 for
+    conflicts (stated deviation: the reference's count at a conflict is order dependent)."""
+    from pdsat_b200 import api, predicter as pr
+    nv, _, offs, lits = bivium
+    stream = list(golden["stream_lits"])
+    sv = pr.schema_vars("bivium_Ending2", k)
+    n = 2000
+    P = oracle_mod.Oracle(nv, offs, lits, "ref" if oracle_mod.have_ref() else "port")
+    P.add_units(stream)
+    conflict, full, trail, sums = P.batch_mt(0, 1, sv, n)
+    cost = np.where(conflict, 0.0, trail.astype(np.float64))
+    ref_sum, ref_med, ref_pred = oracle_mod.predict_mean(cost, k, proc_count=2)
+    solved = int(conflict.sum() + full.sum())
+    ref_prep = oracle_mod.predict_prep(solved, n, k)
+    db = api.ClauseDb(nv, offs, lits, device=0)
+    db.set_fixed_assumptions(stream)
+    res = pr.Predicter(db, cnf_in_set_count=n, evaluation_type="bcp_trail", proc_count=2, base_seed=1).evaluate([sv])[0]
+    assert res.cost.n_conflict == int(conflict.sum()) > 0
+    assert res.sum_cost == ref_sum
+    if ref_pred > 0:
+        assert abs(float((res.predict - np.longdouble(ref_pred)) / np.longdouble(ref_pred))) <= 1e-12
+    else:
+        assert res.predict == 0
+    res = pr.Predicter(db, cnf_in_set_count=n, evaluation_type="prep", base_seed=1).evaluate([sv])[0]
+    assert res.solved == solved
+    assert abs(float((res.predict - np.longdouble(ref_prep)) / np.longdouble(ref_prep))) <= 1e-12
