@@ -87,7 +87,6 @@ static constexpr uint32_t SETCODE_FIXED = 0x80000000u;  // set var already assig
 static constexpr int MAX_PEERS = 16;
 struct PeerDev {
     unsigned long long* shared[MAX_PEERS];  // rank r's receive buffer as mapped in this process
-    unsigned int* cta_done;                 // local ticket counter (last-CTA detection)
     int32_t n_ranks;
     int32_t me;
     int32_t parity;
@@ -105,7 +104,10 @@ struct BatchDev {
     uint64_t* words;
     const uint32_t* stream;
     const uint64_t* block_prefix;  // ENUM_BLOCKS prefixes, all points
-    unsigned long long* cost;   // n_points * 8
+    unsigned long long* cost;   // n_points * 8: the published accumulators (output)
+    unsigned long long* acc;    // n_points * 8: scratch the warps add into; zero between launches (the
+                                // last CTA publishes it into `cost` and clears it: no memset per step)
+    unsigned int* cta_done;     // ticket counter (last-CTA detection)
     uint64_t* conflict_bits;    // per global group (optional)
     uint64_t* full_bits;        // per global group (optional)
     uint32_t* trail;            // per global group * 64 (optional)
@@ -1026,7 +1028,7 @@ __device__ __forceinline__ void bcp_body(const DbDev& db, const BatchDev& b, int
             P_cand_cnt = pt->cand_cnt;
             P_flags = pt->flags;
             P_code0 = lane < (int)k ? b.setcode[P_var_off + lane] : 0u;
-            flush_acc(accs, p_prev, b.cost, lane);
+            flush_acc(accs, p_prev, b.acc, lane);
             p_prev = p;
         }
         // BCP can only start from a candidate record or a contradicted level-0 value (a set that
@@ -1333,7 +1335,7 @@ __device__ __forceinline__ void bcp_body(const DbDev& db, const BatchDev& b, int
                 PT* dst = (PT*)(b.assign + g * (uint64_t)db.n_lit);  // 64-bit planes per literal; a half fills its word half
                 for (int i = lane; i < db.n_lit; i += 32) dst[(size_t)i * HALVES + half] = c.S[i];
             }
-            if (fullm) {
+            if (fullm && b.max_models > 0) {
                 // models found by BCP alone (mpi_predicter.cpp:755-762 b_SAT_set_array)
                 uint64_t rem = fullm;
                 while (rem) {
@@ -1389,18 +1391,21 @@ __device__ __forceinline__ void bcp_body(const DbDev& db, const BatchDev& b, int
             b.full_bits[g] = full64;
         }
     }
-    flush_acc(accs, p_prev, b.cost, lane);
+    flush_acc(accs, p_prev, b.acc, lane);
 
-    if (b.peer.n_ranks > 0) {
-        // the last CTA of this rank exchanges the rank's sums with every peer (see PeerDev)
+    // ---- the last CTA publishes the accumulators: alone, or after the exchange with the peers
+    {
         __shared__ unsigned int s_ticket;
         __threadfence();
         __syncthreads();
-        if (threadIdx.x == 0) s_ticket = atomicAdd(b.peer.cta_done, 1u);
+        if (threadIdx.x == 0) s_ticket = atomicAdd(b.cta_done, 1u);
         __syncthreads();
-        if (s_ticket == gridDim.x - 1) {
-            __threadfence();
-            const int nw = b.peer.n_words, nr = b.peer.n_ranks, me = b.peer.me;
+        if (s_ticket != gridDim.x - 1) return;
+        __threadfence();
+        const int nw = b.n_points * 8;
+        if (b.peer.n_ranks > 0) {
+            // exchange the rank's sums with every peer (see PeerDev)
+            const int nr = b.peer.n_ranks, me = b.peer.me;
             const uint32_t tag = b.peer.tag;
             const size_t slot = ((size_t)b.peer.parity * MAX_PEERS + me) * 2 * nw;  // my slot in a receive buffer
             // push: packet e of my slot on rank r; every rank starts with a different target so
@@ -1408,11 +1413,11 @@ __device__ __forceinline__ void bcp_body(const DbDev& db, const BatchDev& b, int
             for (int j = threadIdx.x; j < 2 * nw * nr; j += blockDim.x) {
                 const int e = j % (2 * nw);
                 const int r = (j / (2 * nw) + me) % nr;
-                const unsigned long long v = __ldcg(&b.cost[e >> 1]);
+                const unsigned long long v = __ldcg(&b.acc[e >> 1]);
                 const unsigned long long pkt = ((unsigned long long)tag << 32) | (uint32_t)((e & 1) ? (v >> 32) : v);
                 *((volatile unsigned long long*)&b.peer.shared[r][slot + e]) = pkt;
             }
-            __syncthreads();  // all of my sums are on their way before b.cost is overwritten
+            __syncthreads();  // all of my sums are on their way before the scratch is cleared
             // gather: wait for this step's packets of every rank in my own buffer, add, publish
             const volatile unsigned long long* mine = b.peer.shared[me] + (size_t)b.peer.parity * MAX_PEERS * 2 * nw;
             for (int i = threadIdx.x; i < nw; i += blockDim.x) {
@@ -1427,9 +1432,15 @@ __device__ __forceinline__ void bcp_body(const DbDev& db, const BatchDev& b, int
                     sum += (hi << 32) | (uint32_t)lo;
                 }
                 b.cost[i] = sum;
+                b.acc[i] = 0;
             }
-            if (threadIdx.x == 0) *b.peer.cta_done = 0;
+        } else {
+            for (int i = threadIdx.x; i < nw; i += blockDim.x) {
+                b.cost[i] = __ldcg(&b.acc[i]);
+                b.acc[i] = 0;
+            }
         }
+        if (threadIdx.x == 0) *b.cta_done = 0;
     }
 }
 

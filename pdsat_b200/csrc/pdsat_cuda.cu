@@ -99,6 +99,7 @@ struct pdsat_batch {
     uint32_t* d_stream = nullptr;
     unsigned long long* d_cost = nullptr;
     unsigned long long* d_cost_ext = nullptr;
+    unsigned long long* d_acc = nullptr;  // scratch accumulators, zero between launches
     uint64_t* d_conflict = nullptr;
     uint64_t* d_full = nullptr;
     uint32_t* d_trail = nullptr;
@@ -638,6 +639,11 @@ int pdsat_batch_create(pdsat_db* db, int32_t n_points, const pdsat_point* points
     CUB(cudaMalloc(&b->d_words, sizeof(uint64_t) * words));
     CUB(cudaMalloc(&b->d_stream, sizeof(uint32_t) * (stream_words ? stream_words : 1)));
     CUB(cudaMalloc(&b->d_cost, sizeof(unsigned long long) * PDSAT_COST_WORDS * n_points));
+    CUB(cudaMalloc(&b->d_acc, sizeof(unsigned long long) * PDSAT_COST_WORDS * n_points));
+    CUB(cudaMemset(b->d_acc, 0, sizeof(unsigned long long) * PDSAT_COST_WORDS * n_points));
+    CUB(cudaMemset(b->d_cost, 0, sizeof(unsigned long long) * PDSAT_COST_WORDS * n_points));
+    CUB(cudaMalloc(&b->d_cta_done, sizeof(unsigned int)));
+    CUB(cudaMemset(b->d_cta_done, 0, sizeof(unsigned int)));
     CUB(cudaMalloc(&b->d_model_count, sizeof(unsigned long long)));
     if (b->max_models > 0) {
         CUB(cudaMalloc(&b->d_model_bits, sizeof(uint32_t) * (size_t)b->max_models * b->model_words));
@@ -950,8 +956,8 @@ int pdsat_batch_propagate(pdsat_batch* b) {
     cudaStream_t st = db->stream;
     unsigned long long* cost = b->d_cost_ext ? b->d_cost_ext : b->d_cost;
     CU(cudaEventRecord(b->ev[2], st));
-    CU(cudaMemsetAsync(cost, 0, sizeof(unsigned long long) * PDSAT_COST_WORDS * b->pts.size(), st));
-    CU(cudaMemsetAsync(b->d_model_count, 0, sizeof(unsigned long long), st));
+    // no memset of the accumulators: the kernel's last CTA publishes the scratch sums and clears them
+    if (b->max_models > 0) CU(cudaMemsetAsync(b->d_model_count, 0, sizeof(unsigned long long), st));
     BatchDev bd{};
     bd.points = b->d_points;
     bd.n_points = (int32_t)b->pts.size();
@@ -962,6 +968,8 @@ int pdsat_batch_propagate(pdsat_batch* b) {
     bd.words = b->d_words;
     bd.stream = b->d_stream;
     bd.cost = cost;
+    bd.acc = b->d_acc;
+    bd.cta_done = b->d_cta_done;
     bd.conflict_bits = b->d_conflict;
     bd.full_bits = b->d_full;
     bd.trail = b->d_trail;
@@ -990,7 +998,6 @@ int pdsat_batch_propagate(pdsat_batch* b) {
     const int parity = (int)(b->peer_step & 1);
     if (b->peer_ranks > 0) {
         for (int r = 0; r < b->peer_ranks; r++) bd.peer.shared[r] = b->peer_ptr[r];
-        bd.peer.cta_done = b->d_cta_done;
         bd.peer.n_ranks = b->peer_ranks;
         bd.peer.me = b->peer_me;
         bd.peer.parity = parity;
@@ -1116,7 +1123,14 @@ int pdsat_batch_models(pdsat_batch* b, int64_t* n_found, int32_t* point_of, uint
     if (!b->propagated) return fail(PDSAT_ERR_ARG, "pdsat_batch_models: batch not propagated");
     CU(cudaStreamSynchronize(b->db->stream));
     unsigned long long cnt = 0;
-    CU(cudaMemcpy(&cnt, b->d_model_count, sizeof(cnt), cudaMemcpyDeviceToHost));
+    if (b->max_models > 0) {
+        CU(cudaMemcpy(&cnt, b->d_model_count, sizeof(cnt), cudaMemcpyDeviceToHost));
+    } else {  // nothing is stored: the count is the sum of the points' n_full
+        std::vector<pdsat_cost> c(b->pts.size());
+        unsigned long long* cost = b->d_cost_ext ? b->d_cost_ext : b->d_cost;
+        CU(cudaMemcpy(c.data(), cost, sizeof(pdsat_cost) * c.size(), cudaMemcpyDeviceToHost));
+        for (auto& x : c) cnt += x.n_full;
+    }
     *n_found = (int64_t)cnt;
     const int64_t stored = (int64_t)cnt < b->max_models ? (int64_t)cnt : b->max_models;
     if (stored == 0) return PDSAT_OK;
@@ -1148,8 +1162,6 @@ int pdsat_batch_peer_export(pdsat_batch* b, void* handle_out) {
     if (!b->d_peer_own) {
         CU(cudaMalloc(&b->d_peer_own, sizeof(unsigned long long) * words));
         CU(cudaMemset(b->d_peer_own, 0, sizeof(unsigned long long) * words));
-        CU(cudaMalloc(&b->d_cta_done, sizeof(unsigned int)));
-        CU(cudaMemset(b->d_cta_done, 0, sizeof(unsigned int)));
     }
     cudaIpcMemHandle_t hd;
     CU(cudaIpcGetMemHandle(&hd, b->d_peer_own));
@@ -1211,6 +1223,7 @@ void pdsat_batch_destroy(pdsat_batch* b) {
     cudaFree(b->d_words);
     cudaFree(b->d_stream);
     cudaFree(b->d_cost);
+    cudaFree(b->d_acc);
     cudaFree(b->d_conflict);
     cudaFree(b->d_full);
     cudaFree(b->d_trail);
