@@ -187,14 +187,63 @@ __global__ void fill_words_kernel(BatchDev b) {
 #pragma unroll 8
             for (int s = 0; s < 64; s++) out |= (((lint + s) >> j) & 1ull) << s;
         }
-    } else {  // packed sample-major value stream (mt19937 bits or caller's explicit values)
-        const uint32_t* st = b.stream + pt.stream_off;
-        uint64_t n = pt.n_samples - s0;
-        int ns = n < 64 ? (int)n : 64;
-        uint64_t d = pt.stream_skip + s0 * pt.k + j;
-        for (int s = 0; s < ns; s++, d += pt.k) out |= (uint64_t)((__ldg(&st[d >> 5]) >> (d & 31)) & 1u) << s;
+    } else {  // packed sample-major value stream: fill_stream_kernel writes these words
+        return;
     }
     b.words[w] = out;
+}
+
+// 32 x 32 bit transpose across a warp: lane r holds row r; afterwards bit r of lane c is the
+// old bit c of lane r (recursive swap of the off-diagonal blocks, 5 shuffles).
+__device__ __forceinline__ uint32_t warp_transpose32(uint32_t x, int lane) {
+#pragma unroll
+    for (int j = 16; j >= 1; j >>= 1) {
+        const uint32_t m = j == 16 ? 0x0000FFFFu : j == 8 ? 0x00FF00FFu : j == 4 ? 0x0F0F0F0Fu : j == 2 ? 0x33333333u : 0x55555555u;
+        const uint32_t y = __shfl_xor_sync(0xffffffffu, x, j);
+        x = (lane & j) ? ((x & ~m) | ((y >> j) & m)) : ((x & m) | ((y & m) << j));
+    }
+    return x;
+}
+
+// Assumption words of the points whose values come as a packed sample-major bit stream
+// (mt19937 bits, or the caller's explicit values): draw (s, j) = bit s*k + j of the point's
+// window.  One warp per sample group: lane s pulls the k-bit row of samples s and s+32 out of
+// the stream 32 columns at a time, two warp transposes turn the 64 x 32 block into the 32
+// output words of those columns (bit s of word j = value of set variable j in sample s).
+static constexpr int FILL_STREAM_WARPS = 8;
+__global__ void __launch_bounds__(FILL_STREAM_WARPS * 32) fill_stream_kernel(BatchDev b) {
+    const uint64_t g = (uint64_t)blockIdx.x * FILL_STREAM_WARPS + (threadIdx.x >> 5);
+    if (g >= b.n_groups) return;
+    const int lane = threadIdx.x & 31;
+    const PointDev& pt = b.points[find_point(b.points, b.n_points, g)];
+    if (pt.mode != 0 && pt.mode != 3) return;  // PDSAT_MODE_RANDOM_MT19937 / PDSAT_MODE_EXPLICIT
+    const uint64_t gi = g - pt.group_start;
+    const uint64_t s0 = gi * 64;
+    const uint64_t left = pt.n_samples - s0;
+    const uint32_t ns = left < 64 ? (uint32_t)left : 64u;
+    const uint32_t k = pt.k;
+    const uint32_t* st = b.stream + pt.stream_off;
+    uint64_t* dst = b.words + pt.word_off + gi * pt.kp;
+    const uint64_t d0 = pt.stream_skip + s0 * k;
+    for (uint32_t c = 0; c < pt.kp; c += 32) {
+        const uint32_t nb = c < k ? (k - c < 32 ? k - c : 32u) : 0u;  // columns of this block
+        uint32_t half[2];
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const uint32_t s = lane + 32 * h;
+            uint32_t row = 0;
+            if (s < ns && nb) {
+                const uint64_t d = d0 + (uint64_t)s * k + c;
+                const uint32_t sh = (uint32_t)(d & 31);
+                const uint32_t lo = __ldg(st + (d >> 5));
+                const uint32_t hi = sh + nb > 32 ? __ldg(st + (d >> 5) + 1) : 0u;
+                row = __funnelshift_r(lo, hi, sh);
+                if (nb < 32) row &= (1u << nb) - 1u;
+            }
+            half[h] = warp_transpose32(row, lane);
+        }
+        if (c + lane < pt.kp) dst[c + lane] = (uint64_t)half[0] | ((uint64_t)half[1] << 32);
+    }
 }
 
 // ------------------------------------------------------------------ mt19937
@@ -205,120 +254,162 @@ struct MtSegment {
     uint32_t pad;
 };
 
-// One jump-ahead: state[dst] = g(A) state[src], g = polys[poly] (x^(624*2^t) mod phi as
-// 19968 bits): out[w] = XOR over the set bits i of g of x[i + w], where x[0..623] is the source
-// window and x continues by the mt19937 recurrence (mt_jump.hpp).
-// A state slot is stored as MT_PARTS partial vectors whose XOR is the state: a jump is split
-// over MT_PARTS CTAs, CTA q handling the polynomial bits [q*3328, (q+1)*3328) and writing
-// partial vector q of dst (no atomics, no zeroing; consumers XOR the parts on load).  This cuts
-// the latency of a level of the jump tree by ~6x, which matters because the first levels have
-// only 1, 2, 4 ... jumps.
+// One jump-ahead: state[dst] = g(A) state[src], g = polys[poly] (x^J mod phi as 19937 bits):
+// out[w] = XOR over the set bits i of g of x[i + w], where x[0..623] is the source window and
+// x continues by the mt19937 recurrence (mt_jump.hpp).  Two kernels per level of the jump tree:
+//   mt19937_seq_kernel   one CTA per SOURCE state runs the recurrence and writes x[0 .. MT_SEQ_WORDS)
+//   mt19937_corr_kernel  MT_PARTS CTAs per jump; CTA q correlates the polynomial bits
+//                        [q*MT_CORR_CTA_BITS, (q+1)*MT_CORR_CTA_BITS) against its stretch of x
+// Several jumps of one level start from the same source (the tree has radix 8): they share the
+// sequence.  A state slot is stored as MT_PARTS partial vectors whose XOR is the state (CTA q
+// writes partial vector q of dst: no atomics, no zeroing; consumers XOR the parts on load).
 struct MtJumpTask {
-    uint32_t src, dst, poly, pad;
+    uint32_t seq;   // which sequence of the level's mt19937_seq_kernel launch
+    uint32_t dst;   // state slot written
+    uint32_t poly;  // slot of the jump polynomial
+    uint32_t pad;
 };
 
-static constexpr int MT_PARTS = 6;            // CTAs per jump = partial vectors per state slot
-static constexpr int MT_JUMP_SLICE_WORDS = 104;  // polynomial words per CTA (624 / 6)
-static constexpr int MT_JUMP_SUB = 6;         // sub-slices inside a CTA (3 warps each)
-static constexpr int MT_JUMP_V = 8;           // output words per thread (register window)
-static constexpr int MT_JUMP_THREADS = MT_JUMP_SUB * 96;  // 78 of every 96 threads carry outputs
-static constexpr int MT_JUMP_ROUNDS = 34;     // 34 * 624 = 21216 >= 19968 + 8 + 623 words
-static constexpr int MT_JUMP_SMEM = (MT_JUMP_ROUNDS * 624 + MT_JUMP_SLICE_WORDS) * 4;
+static constexpr int MT_PARTS = 10;           // CTAs per jump = partial vectors per state slot
+static constexpr int MT_CORR_V = 20;          // output words per lane: one WARP covers 32*20 >= 624 outputs
+static constexpr int MT_CORR_WARPS = 10;      // warps per CTA, each with its own polynomial bits
+static constexpr int MT_CORR_BLOCKS = 10;     // 20-bit blocks per warp (a block = 10 steps of 2 bits)
+static constexpr int MT_CORR_WARP_BITS = MT_CORR_BLOCKS * 20;               // 200
+static constexpr int MT_CORR_CTA_BITS = MT_CORR_WARPS * MT_CORR_WARP_BITS;  // 2000; x MT_PARTS = 20000 >= 19937
+static constexpr int MT_CORR_X_WORDS = MT_CORR_CTA_BITS + 32 * MT_CORR_V + 4;  // stretch of x one CTA reads
+static constexpr int MT_SEQ_ROUNDS = 34;
+static constexpr int MT_SEQ_WORDS = MT_SEQ_ROUNDS * 624;  // 21216 >= 20000 + 644
+static constexpr int MT_SEQ_THREADS = 256;
+static constexpr int MT_SEQ_SMEM = MT_SEQ_WORDS * 4;
+static_assert(MT_PARTS * MT_CORR_CTA_BITS >= 19937, "polynomial bits not covered");
+static_assert((MT_PARTS - 1) * MT_CORR_CTA_BITS + MT_CORR_X_WORDS <= MT_SEQ_WORDS, "sequence too short");
 
 __device__ __forceinline__ size_t mt_state_off(uint32_t slot, int part) {
     return ((size_t)slot * MT_PARTS + part) * 624;
 }
 
-__global__ void __launch_bounds__(MT_JUMP_THREADS) mt19937_jump_kernel(const uint32_t* __restrict__ polys,
-                                                                       uint32_t* __restrict__ states,
-                                                                       const MtJumpTask* __restrict__ tasks) {
-    extern __shared__ uint32_t jsm[];
-    uint32_t* x = jsm;                         // the sequence, as far as this slice needs it
-    uint32_t* g = jsm + MT_JUMP_ROUNDS * 624;  // this CTA's 104 words of polynomial bits
+// x[n + 624] = x[n + 397] ^ twist(x[n], x[n + 1]), 227 words per phase (x[n + 397] of the
+// last word of a phase is the newest word of the phase before).  The sequence stays in shared
+// memory until the end.
+__global__ void __launch_bounds__(MT_SEQ_THREADS) mt19937_seq_kernel(const uint32_t* __restrict__ states,
+                                                                     const uint32_t* __restrict__ srcs,
+                                                                     uint32_t* __restrict__ seq) {
+    extern __shared__ __align__(16) uint32_t sx[];
     const int tid = threadIdx.x;
-    const MtJumpTask t = tasks[blockIdx.x / MT_PARTS];
-    const int q = blockIdx.x % MT_PARTS;
-    for (int i = tid; i < 624; i += MT_JUMP_THREADS) {
+    const uint32_t src = srcs[blockIdx.x];
+    for (int i = tid; i < 624; i += MT_SEQ_THREADS) {
         uint32_t v = 0;
 #pragma unroll
-        for (int p = 0; p < MT_PARTS; p++) v ^= states[mt_state_off(t.src, p) + i];
-        x[i] = v;
-    }
-    if (tid < MT_JUMP_SLICE_WORDS) g[tid] = polys[(size_t)t.poly * 624 + q * MT_JUMP_SLICE_WORDS + tid];
-    __syncthreads();
-    // run the recurrence forward: x[n+624] = x[n+397] ^ twist(x[n], x[n+1]); slice q reads
-    // x[0 .. (q+1)*3328 + 8 + 623]
-    const int rounds = ((q + 1) * MT_JUMP_SLICE_WORDS * 32 + MT_JUMP_V + 624 + 623) / 624;
-    for (int r = 0; r < rounds - 1; r++) {
-        uint32_t* cur = x + r * 624;
-        const int base[3] = {0, 227, 454};
-        const int cnt[3] = {227, 227, 170};
-#pragma unroll
-        for (int ph = 0; ph < 3; ph++) {
-            if (tid < cnt[ph]) {
-                const int n = base[ph] + tid;
-                const uint32_t y = (cur[n] & 0x80000000u) | (cur[n + 1] & 0x7fffffffu);
-                cur[n + 624] = cur[n + 397] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
-            }
-            __syncthreads();
-        }
-    }
-    // correlation: thread (sub-slice s, tp) accumulates output words 8*tp .. 8*tp+7 over the
-    // polynomial words [sb, se) of this CTA's slice, sliding an 8-word register window
-    const int s = tid / 96, tp = tid % 96;
-    const int sb = (s * MT_JUMP_SLICE_WORDS) / MT_JUMP_SUB, se = ((s + 1) * MT_JUMP_SLICE_WORDS) / MT_JUMP_SUB;
-    uint32_t acc[MT_JUMP_V];
-#pragma unroll
-    for (int v = 0; v < MT_JUMP_V; v++) acc[v] = 0;
-    if (tp < 78) {
-        const int w0 = tp * MT_JUMP_V;
-        const uint32_t* xs = x + w0 + (q * MT_JUMP_SLICE_WORDS + sb) * 32;
-        uint32_t r[MT_JUMP_V];
-#pragma unroll
-        for (int v = 0; v < MT_JUMP_V; v++) r[v] = xs[v];
-        for (int gi = sb; gi < se; gi++) {
-            const uint32_t gw = g[gi];
-            const uint32_t* xw = xs + (gi - sb) * 32 + MT_JUMP_V;
-            // two polynomial bits per step; the bits are warp-uniform, so the 4-way switch is
-            // a uniform branch and a step costs at most ONE 3-input XOR per output word
-#pragma unroll
-            for (int b = 0; b < 32; b += 2) {
-                const uint32_t t0 = xw[b], t1 = xw[b + 1];  // words entering the window
-                switch ((gw >> b) & 3u) {
-                    case 1:
-#pragma unroll
-                        for (int v = 0; v < MT_JUMP_V; v++) acc[v] ^= r[(b + v) % MT_JUMP_V];
-                        break;
-                    case 2:
-#pragma unroll
-                        for (int v = 0; v < MT_JUMP_V; v++)
-                            acc[v] ^= v < MT_JUMP_V - 1 ? r[(b + 1 + v) % MT_JUMP_V] : t0;
-                        break;
-                    case 3:
-#pragma unroll
-                        for (int v = 0; v < MT_JUMP_V; v++)
-                            acc[v] ^= r[(b + v) % MT_JUMP_V] ^ (v < MT_JUMP_V - 1 ? r[(b + 1 + v) % MT_JUMP_V] : t0);
-                        break;
-                    default:
-                        break;
-                }
-                r[b % MT_JUMP_V] = t0;
-                r[(b + 1) % MT_JUMP_V] = t1;
-            }
-        }
-    }
-    __syncthreads();  // everyone is done reading x: reuse its head for the partial sums
-    if (tp < 78) {
-#pragma unroll
-        for (int v = 0; v < MT_JUMP_V; v++) x[s * 624 + tp * MT_JUMP_V + v] = acc[v];
+        for (int p = 0; p < MT_PARTS; p++) v ^= states[mt_state_off(src, p) + i];
+        sx[i] = v;
     }
     __syncthreads();
-    for (int w = tid; w < 624; w += MT_JUMP_THREADS) {
+    for (int n0 = 0; n0 < MT_SEQ_WORDS - 624; n0 += 227) {
+        const int n = n0 + tid;
+        if (tid < 227 && n < MT_SEQ_WORDS - 624) {
+            const uint32_t a = sx[n], b = sx[n + 1], m = sx[n + 397];
+            const uint32_t y = (a & 0x80000000u) | (b & 0x7fffffffu);
+            sx[n + 624] = m ^ (y >> 1) ^ ((0u - (b & 1u)) & 0x9908b0dfu);
+        }
+        __syncthreads();
+    }
+    uint4* out = reinterpret_cast<uint4*>(seq + (size_t)blockIdx.x * MT_SEQ_WORDS);
+    const uint4* in = reinterpret_cast<const uint4*>(sx);
+    for (int i = tid; i < MT_SEQ_WORDS / 4; i += MT_SEQ_THREADS) out[i] = in[i];
+}
+
+// acc[v] ^= XOR over the set bits j of the 2-bit digit P of e[v + j], where e[0..19] is the
+// lane's register window (element i in r[(2*S + i) % 20], S = step inside the 20-bit block)
+// and e[20] is the first of the two words entering it.  Two bits per step keep the unrolled
+// body (10 steps x 3 cases) small enough for the instruction cache: with 4-bit digits the
+// warps spent 8 of 10 cycles waiting for instructions.
+template <int P, int S>
+__device__ __forceinline__ void mt_corr_apply(uint32_t (&acc)[MT_CORR_V], const uint32_t (&r)[MT_CORR_V], uint32_t in0) {
+#pragma unroll
+    for (int v = 0; v < MT_CORR_V; v++) {
+        uint32_t a = acc[v];
+        if (P & 1) a ^= r[(2 * S + v) % 20];
+        if (P & 2) a ^= v + 1 < 20 ? r[(2 * S + v + 1) % 20] : in0;
+        acc[v] = a;
+    }
+}
+
+template <int S>
+__device__ __forceinline__ void mt_corr_step(uint32_t digit, uint32_t (&acc)[MT_CORR_V], uint32_t (&r)[MT_CORR_V],
+                                             uint32_t in0, uint32_t in1) {
+    // the digit is warp-uniform: one uniform branch, then one XOR per output word
+    if (digit == 1) mt_corr_apply<1, S>(acc, r, in0);
+    else if (digit == 2) mt_corr_apply<2, S>(acc, r, in0);
+    else if (digit == 3) mt_corr_apply<3, S>(acc, r, in0);
+    r[(2 * S) % 20] = in0;
+    r[(2 * S + 1) % 20] = in1;
+}
+
+__global__ void __launch_bounds__(MT_CORR_WARPS * 32, 2) mt19937_corr_kernel(const uint32_t* __restrict__ polys,
+                                                                             uint32_t* __restrict__ states,
+                                                                             const MtJumpTask* __restrict__ tasks,
+                                                                             const uint32_t* __restrict__ seq) {
+    __shared__ __align__(16) uint32_t x[MT_CORR_X_WORDS];
+    __shared__ uint32_t g[MT_CORR_CTA_BITS / 32 + 2];
+    __shared__ uint32_t red[MT_CORR_WARPS][MT_CORR_V * 33];  // [warp][v * 33 + lane]: conflict-free both ways
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int task = blockIdx.x / MT_PARTS, q = blockIdx.x % MT_PARTS;
+    const MtJumpTask t = tasks[task];
+    const int bit0 = q * MT_CORR_CTA_BITS;  // first polynomial bit of this CTA (a multiple of 4)
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(seq + (size_t)t.seq * MT_SEQ_WORDS + bit0);
+        uint4* dst = reinterpret_cast<uint4*>(x);
+        for (int i = tid; i < MT_CORR_X_WORDS / 4; i += MT_CORR_WARPS * 32) dst[i] = __ldg(src + i);
+    }
+    const int gw0 = bit0 >> 5;
+    if (tid < MT_CORR_CTA_BITS / 32 + 2) g[tid] = gw0 + tid < 624 ? polys[(size_t)t.poly * 624 + gw0 + tid] : 0u;
+    __syncthreads();
+
+    uint32_t acc[MT_CORR_V], r[MT_CORR_V];
+    const uint32_t* xs = x + warp * MT_CORR_WARP_BITS + lane * MT_CORR_V;  // the lane's window at the warp's first bit
+#pragma unroll
+    for (int v = 0; v < MT_CORR_V; v += 4) {
+        const uint4 w = *reinterpret_cast<const uint4*>(xs + v);
+        r[v] = w.x, r[v + 1] = w.y, r[v + 2] = w.z, r[v + 3] = w.w;
+        acc[v] = acc[v + 1] = acc[v + 2] = acc[v + 3] = 0;
+    }
+    for (int blk = 0; blk < MT_CORR_BLOCKS; blk++) {
+        const int rel = (bit0 & 31) + warp * MT_CORR_WARP_BITS + blk * 20;  // bit offset inside g[]
+        const uint32_t dw = __funnelshift_r(g[rel >> 5], g[(rel >> 5) + 1], rel & 31);
+        const uint4* xin = reinterpret_cast<const uint4*>(xs + blk * 20 + MT_CORR_V);
+        uint4 t4 = xin[0];
+        mt_corr_step<0>(dw & 3u, acc, r, t4.x, t4.y);
+        mt_corr_step<1>((dw >> 2) & 3u, acc, r, t4.z, t4.w);
+        t4 = xin[1];
+        mt_corr_step<2>((dw >> 4) & 3u, acc, r, t4.x, t4.y);
+        mt_corr_step<3>((dw >> 6) & 3u, acc, r, t4.z, t4.w);
+        t4 = xin[2];
+        mt_corr_step<4>((dw >> 8) & 3u, acc, r, t4.x, t4.y);
+        mt_corr_step<5>((dw >> 10) & 3u, acc, r, t4.z, t4.w);
+        t4 = xin[3];
+        mt_corr_step<6>((dw >> 12) & 3u, acc, r, t4.x, t4.y);
+        mt_corr_step<7>((dw >> 14) & 3u, acc, r, t4.z, t4.w);
+        t4 = xin[4];
+        mt_corr_step<8>((dw >> 16) & 3u, acc, r, t4.x, t4.y);
+        mt_corr_step<9>((dw >> 18) & 3u, acc, r, t4.z, t4.w);
+    }
+#pragma unroll
+    for (int v = 0; v < MT_CORR_V; v++) red[warp][v * 33 + lane] = acc[v];
+    __syncthreads();
+    for (int w = tid; w < 624; w += MT_CORR_WARPS * 32) {
+        const int idx = (w % MT_CORR_V) * 33 + w / MT_CORR_V;  // output w = word v of lane w / 20
         uint32_t o = 0;
 #pragma unroll
-        for (int ss = 0; ss < MT_JUMP_SUB; ss++) o ^= x[ss * 624 + w];
+        for (int ww = 0; ww < MT_CORR_WARPS; ww++) o ^= red[ww][idx];
         states[mt_state_off(t.dst, q) + w] = o;
     }
+}
+
+// one level of jumps: n_src sequences, n jumps reading them (MtJumpTask::seq < n_src)
+static inline void mt19937_launch_jumps(const uint32_t* polys, uint32_t* states, const uint32_t* srcs, size_t n_src,
+                                        const MtJumpTask* tasks, size_t n, uint32_t* seq, cudaStream_t st) {
+    mt19937_seq_kernel<<<(unsigned)n_src, MT_SEQ_THREADS, MT_SEQ_SMEM, st>>>(states, srcs, seq);
+    mt19937_corr_kernel<<<(unsigned)(n * MT_PARTS), MT_CORR_WARPS * 32, 0, st>>>(polys, states, tasks, seq);
 }
 
 // ---- warp-register mt19937: one WARP per stream segment, the 624-word state lives in 20
@@ -328,16 +419,20 @@ __global__ void __launch_bounds__(MT_JUMP_THREADS) mt19937_jump_kernel(const uin
 // Per draw only the bool_rand bit is needed: bool_rand == !(tempered >> 31), and bit 31 of the
 // tempered word is parity(y & 0x89010000) of the raw word y (bits 31, 27, 24, 16 - follows
 // from the four tempering shifts/masks).  Bits are packed little-endian, 39 words per 2 rounds.
+// The loop is bound by the ALU pipe (one warp instruction per two cycles per scheduler), so
+// the update keeps that pipe's share small: one bit-select LOP3 for the twist input, the
+// matrix term and the parity as integer multiplies (FMA pipe), the ballot word stored by lane
+// 0 as it is produced instead of being routed to a lane with a compare + select per chunk.
 struct MtWarp {
     uint32_t R[20];
-    uint32_t carry;         // pending low half-word of an odd round
-    uint32_t keepA, keepB;  // lane i holds output word i (keepA) / 32+i (keepB) of the round pair
+    uint32_t carry;  // pending low half-word of an odd round
+    uint32_t* dst;   // output words of the current round pair
+    bool store;      // lane 0 of a live segment
     int lane;
 
     template <int IDX>
     __device__ __forceinline__ void emit(uint32_t word) {
-        if (IDX < 32) keepA = lane == IDX ? word : keepA;
-        else keepB = lane == IDX - 32 ? word : keepB;
+        if (store) dst[IDX] = word;
     }
     // neighbours of chunk C: b = mt[k+1], m = mt[(k+397) % 624] for k = 32C + lane
     template <int C>
@@ -363,12 +458,17 @@ struct MtWarp {
     }
     template <int C, int ODD>
     __device__ __forceinline__ void update(uint32_t b, uint32_t m) {
-        const uint32_t a = R[C];
-        const uint32_t y = (a & 0x80000000u) | (b & 0x7fffffffu);
-        const uint32_t nv = m ^ (y >> 1) ^ ((0u - (b & 1u)) & 0x9908b0dfu);
+        uint32_t y;  // (mt[k] & 0x80000000) | (mt[k+1] & 0x7fffffff) as one bit-select
+        asm("lop3.b32 %0, %1, %2, 0x80000000, 0xE4;" : "=r"(y) : "r"(R[C]), "r"(b));
+        uint32_t mag;  // (mt[k+1] & 1) ? 0x9908b0df : 0 as a multiply (inline PTX: the compiler would turn it into compare + select)
+        asm("mul.lo.u32 %0, %1, 0x9908b0df;" : "=r"(mag) : "r"(b & 1u));
+        const uint32_t nv = m ^ (y >> 1) ^ mag;
         R[C] = nv;
-        const uint32_t bit = (__popc(nv & 0x89010000u) & 1u) ^ 1u;
-        uint32_t w = __ballot_sync(0xffffffffu, bit);
+        // parity of bits 31, 27, 24, 16 = bit 31 of the product with 2^0 + 2^4 + 2^7 + 2^15: the
+        // four bits meet at position 31, the other partial products fall on distinct lower bits
+        int32_t par;
+        asm("mul.lo.s32 %0, %1, 0x8091;" : "=r"(par) : "r"(nv & 0x89010000u));
+        uint32_t w = __ballot_sync(0xffffffffu, par >= 0);
         if (C == 19) w &= 0xffffu;
         if (!ODD) {
             if (C < 19) emit<C>(w);
@@ -423,16 +523,12 @@ __global__ void __launch_bounds__(MT_BITS_WARPS * 32) mt19937_bits_kernel(const 
         g.R[c] = v;
     }
     g.carry = 0;
-    g.keepA = g.keepB = 0;
-    uint32_t* dst = out + seg.out_off + g.lane;
+    g.store = live && g.lane == 0;
+    g.dst = out + seg.out_off;
     for (uint32_t r = 0; r < n_rounds; r += 2) {
         g.round<0>();
         g.round<1>();
-        if (live) {
-            dst[0] = g.keepA;
-            if (g.lane < 7) dst[32] = g.keepB;
-        }
-        dst += 39;
+        g.dst += 39;
     }
 }
 

@@ -54,15 +54,29 @@ struct pdsat_db {
     CdclPool cdcl;  // host solvers for the hand-off (lazy)
     int live_batches = 0;
     bool zombie = false;  // pdsat_destroy was called while batches were alive
-    // mt19937 jump polynomials x^(624*2^t) mod phi resident on the device (lazy)
+    // mt19937 jump polynomials x^(624*rounds) mod phi resident on the device (lazy), by round
+    // count: powers of two and small multiples of them (the levels of the jump tree), and the
+    // composite polynomials of stream offsets that keep coming back (a rank's shard offset)
     uint32_t* d_polys = nullptr;
-    int n_polys = 0;
-    // composite polynomials x^(624*R0) for stream offsets that keep coming back (a rank's
-    // shard offset): slot MAX_POLYS + i of d_polys
-    std::map<uint64_t, int> comp_slot, comp_seen;
+    std::map<uint64_t, int> poly_slots, comp_seen;
 };
-static constexpr int MAX_POLYS = 64;
-static constexpr int MAX_COMP_POLYS = 64;
+static constexpr int POLY_CAP = 512;            // slots of d_polys
+static constexpr int POLY_CAP_COMPOSITE = 448;  // composite offsets stop here: the rest stays free for the tree
+
+// slot of x^(624*rounds) mod phi on the device (uploaded on first use); -1 = table full
+static int mt_poly_slot(pdsat_db* db, uint64_t rounds, cudaStream_t st) {
+    auto it = db->poly_slots.find(rounds);
+    if (it != db->poly_slots.end()) return it->second;
+    if ((int)db->poly_slots.size() >= POLY_CAP) return -1;
+    if (!db->d_polys && cudaMalloc(&db->d_polys, sizeof(uint32_t) * 624 * POLY_CAP) != cudaSuccess) return -1;
+    const uint32_t* pl = __builtin_popcountll(rounds) == 1 ? MtJumpPolys::instance().poly(__builtin_ctzll(rounds))
+                                                           : MtJumpPolys::instance().poly_for_rounds(rounds);
+    const int slot = (int)db->poly_slots.size();
+    if (cudaMemcpyAsync(db->d_polys + (size_t)slot * 624, pl, sizeof(uint32_t) * 624, cudaMemcpyHostToDevice, st) != cudaSuccess)
+        return -1;
+    db->poly_slots.emplace(rounds, slot);
+    return slot;
+}
 
 struct HostPoint {
     std::vector<int32_t> set_vars;
@@ -115,6 +129,8 @@ struct pdsat_batch {
     MtSegment* h_mt_segs = nullptr;   // pinned
     MtJumpTask* d_mt_tasks = nullptr;
     MtJumpTask* h_mt_tasks = nullptr; // pinned
+    uint32_t* d_mt_srcs = nullptr;    // source slots of the sequences, level by level
+    uint32_t* h_mt_srcs = nullptr;    // pinned
     size_t mt_tasks_cap = 0;
     int n_mt_points = 0;
     int n_mt_segs = 0;
@@ -132,6 +148,8 @@ struct pdsat_batch {
     unsigned long long* d_peer_own = nullptr;          // this rank's IPC-exported buffer
     unsigned long long* peer_ptr[MAX_PEERS] = {};      // every rank's buffer as mapped here
     unsigned int* d_cta_done = nullptr;
+    uint32_t* d_mt_seq = nullptr;  // sequences of one level of jump-aheads (mt19937_seq_kernel)
+    size_t mt_seq_cap = 0;
     int peer_ranks = 0, peer_me = 0;
     uint64_t peer_step = 0;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -439,7 +457,7 @@ static void mt_plan(HostPoint& hp) {
 static int mt_target_segments() {
     const char* e = getenv("PDSAT_MT_SEGMENTS");
     int t = e ? atoi(e) : 0;
-    return t > 0 ? t : 592;  // 4 CTAs per SM on a 148-SM part
+    return t > 0 ? t : 1184;  // 2 warps per scheduler on a 148-SM part
 }
 
 int pdsat_batch_create(pdsat_db* db, int32_t n_points, const pdsat_point* points, uint32_t out_flags,
@@ -665,6 +683,8 @@ int pdsat_batch_create(pdsat_db* db, int32_t n_points, const pdsat_point* points
         b->mt_tasks_cap = (size_t)b->n_mt_segs + 64 * (size_t)b->n_mt_points;
         CUB(cudaMalloc(&b->d_mt_tasks, sizeof(MtJumpTask) * b->mt_tasks_cap));
         CUB(cudaMallocHost(&b->h_mt_tasks, sizeof(MtJumpTask) * b->mt_tasks_cap));
+        CUB(cudaMalloc(&b->d_mt_srcs, sizeof(uint32_t) * b->mt_tasks_cap));
+        CUB(cudaMallocHost(&b->h_mt_srcs, sizeof(uint32_t) * b->mt_tasks_cap));
         for (auto& hp : b->pts) {
             if (hp.mode != PDSAT_MODE_RANDOM_MT19937) continue;
             for (uint32_t j = 0; j < hp.n_segs; j++) {
@@ -676,7 +696,12 @@ int pdsat_batch_create(pdsat_db* db, int32_t n_points, const pdsat_point* points
             }
         }
         CUB(cudaMemcpy(b->d_mt_segs, b->h_mt_segs, sizeof(MtSegment) * b->n_mt_segs, cudaMemcpyHostToDevice));
-        CUB(cudaFuncSetAttribute(mt19937_jump_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MT_JUMP_SMEM));
+        // scratch for the sequences of one level of jumps (at most one jump per segment pair / point)
+        size_t max_jumps = (size_t)(b->n_mt_segs + 1) / 2;
+        if ((size_t)b->n_mt_points > max_jumps) max_jumps = (size_t)b->n_mt_points;
+        CUB(cudaMalloc(&b->d_mt_seq, sizeof(uint32_t) * MT_SEQ_WORDS * max_jumps));
+        CUB(cudaFuncSetAttribute(mt19937_seq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MT_SEQ_SMEM));
+        b->mt_seq_cap = max_jumps;
     }
     if (b->n_blocks_total) {
         CUB(cudaMalloc(&b->d_blocks, sizeof(uint64_t) * b->n_blocks_total));
@@ -814,7 +839,6 @@ int pdsat_batch_fill(pdsat_batch* b) {
     if (b->n_mt_segs) {
         // seed states -> part 0 of slot 2p (other parts zero); jump-ahead (mt_jump.hpp) places
         // every other segment
-        int max_poly = -1;
         for (auto& hp : b->pts) {
             if (hp.mode != PDSAT_MODE_RANDOM_MT19937) continue;
             mt19937_seed((uint32_t)hp.seed, b->h_mt_states + (size_t)hp.mt_index * 624);
@@ -823,51 +847,50 @@ int pdsat_batch_fill(pdsat_batch* b) {
         CU(cudaMemcpy2DAsync(b->d_mt_states, sizeof(uint32_t) * 624 * MT_PARTS * 2, b->h_mt_states, sizeof(uint32_t) * 624,
                              sizeof(uint32_t) * 624, b->n_mt_points, cudaMemcpyHostToDevice, st));
         h2d += (int64_t)(sizeof(uint32_t) * 624 * b->n_mt_points + sizeof(MtSegment) * b->n_mt_segs);
-        // launch plan: (a) per set bit t of the first round, a jump by 2^t rounds between the
-        // point's two slots; (b) binary tree over the segments, top level first
-        struct Launch { size_t off, cnt; };
+        // launch plan: (a) the jump to the first round of every point's window: per set bit t
+        // of the round number a jump by 2^t rounds between the point's two slots - or ONE jump
+        // with the composite polynomial (built on the host once, ~0.1 s) for an offset seen for
+        // the second time; (b) a radix-8 tree over the segments, top level first: the up to 7
+        // jumps that leave a segment share its sequence
+        struct Launch { size_t off, cnt, src_off, src_cnt; };
         std::vector<Launch> launches;
-        size_t nt = 0;
+        size_t nt = 0, ns = 0;
         std::vector<uint32_t> cur_slot(b->pts.size());
         for (size_t p = 0; p < b->pts.size(); p++) cur_slot[p] = 2 * b->pts[p].mt_index;
-        // an offset seen for the second time gets ONE jump with the composite polynomial
-        // x^(624*R0) (built on the host once, ~0.1 s) instead of one jump per set bit
-        if (!db->d_polys) CU(cudaMalloc(&db->d_polys, sizeof(uint32_t) * 624 * (MAX_POLYS + MAX_COMP_POLYS)));
+        bool table_full = false;
+        auto own_seq_task = [&](size_t level_src_off, uint32_t src, uint32_t dst, int poly) {
+            b->h_mt_srcs[ns] = src;
+            b->h_mt_tasks[nt++] = MtJumpTask{(uint32_t)(ns - level_src_off), dst, (uint32_t)poly, 0};
+            ns++;
+        };
         std::vector<char> use_comp(b->pts.size(), 0);
         {
-            size_t start = nt;
+            const size_t start = nt, sstart = ns;
             for (size_t p = 0; p < b->pts.size(); p++) {
                 HostPoint& hp = b->pts[p];
                 const uint64_t r0 = hp.mt_first_round;
                 if (hp.mode != PDSAT_MODE_RANDOM_MT19937 || __builtin_popcountll(r0) < 2) continue;
-                auto it = db->comp_slot.find(r0);
-                if (it == db->comp_slot.end()) {
-                    if (++db->comp_seen[r0] < 2 || (int)db->comp_slot.size() >= MAX_COMP_POLYS) continue;
-                    const int slot = MAX_POLYS + (int)db->comp_slot.size();
-                    CU(cudaMemcpyAsync(db->d_polys + (size_t)slot * 624, MtJumpPolys::instance().poly_for_rounds(r0),
-                                       sizeof(uint32_t) * 624, cudaMemcpyHostToDevice, st));
-                    it = db->comp_slot.emplace(r0, slot).first;
-                }
-                const uint32_t other = cur_slot[p] ^ 1u;
-                b->h_mt_tasks[nt++] = MtJumpTask{cur_slot[p], other, (uint32_t)it->second, 0};
-                cur_slot[p] = other;
+                if (!db->poly_slots.count(r0) && (++db->comp_seen[r0] < 2 || (int)db->poly_slots.size() >= POLY_CAP_COMPOSITE))
+                    continue;
+                const int slot = mt_poly_slot(db, r0, st);
+                if (slot < 0) continue;
+                own_seq_task(sstart, cur_slot[p], cur_slot[p] ^ 1u, slot);
+                cur_slot[p] ^= 1u;
                 use_comp[p] = 1;
             }
-            if (nt > start) launches.push_back({start, nt - start});
+            if (nt > start) launches.push_back({start, nt - start, sstart, ns - sstart});
         }
         for (int t = 0; t < 64; t++) {
-            size_t start = nt;
+            const size_t start = nt, sstart = ns;
             for (size_t p = 0; p < b->pts.size(); p++) {
                 HostPoint& hp = b->pts[p];
                 if (hp.mode != PDSAT_MODE_RANDOM_MT19937 || use_comp[p] || !((hp.mt_first_round >> t) & 1ull)) continue;
-                const uint32_t other = cur_slot[p] ^ 1u;
-                b->h_mt_tasks[nt++] = MtJumpTask{cur_slot[p], other, (uint32_t)t, 0};
-                cur_slot[p] = other;
+                const int slot = mt_poly_slot(db, 1ull << t, st);
+                if (slot < 0) { table_full = true; continue; }
+                own_seq_task(sstart, cur_slot[p], cur_slot[p] ^ 1u, slot);
+                cur_slot[p] ^= 1u;
             }
-            if (nt > start) {
-                launches.push_back({start, nt - start});
-                if (t > max_poly) max_poly = t;
-            }
+            if (nt > start) launches.push_back({start, nt - start, sstart, ns - sstart});
         }
         for (size_t p = 0; p < b->pts.size(); p++)
             if (b->pts[p].mode == PDSAT_MODE_RANDOM_MT19937) b->h_mt_segs[b->pts[p].seg_base].state_idx = cur_slot[p];
@@ -876,38 +899,37 @@ int pdsat_batch_fill(pdsat_batch* b) {
         for (auto& hp : b->pts)
             if (hp.mode == PDSAT_MODE_RANDOM_MT19937 && hp.n_segs > max_segs) max_segs = hp.n_segs;
         int top = 0;
-        while ((2u << top) < max_segs) top++;
+        while ((8ull << (3 * top)) < max_segs) top++;
         for (int lev = top; lev >= 0 && max_segs > 1; lev--) {
-            size_t start = nt;
-            const uint32_t stride = 1u << lev;
+            const size_t start = nt, sstart = ns;
+            const uint64_t stride = 1ull << (3 * lev);
+            if (b->mt_m + 3 * lev > 58) return fail(PDSAT_ERR_LIMIT, "mt19937 stream too long");
             for (size_t p = 0; p < b->pts.size(); p++) {
                 HostPoint& hp = b->pts[p];
                 if (hp.mode != PDSAT_MODE_RANDOM_MT19937) continue;
-                for (uint32_t j = 0; j + stride < hp.n_segs; j += 2 * stride) {
-                    const uint32_t src = j == 0 ? cur_slot[p] : hp.extra_base + j - 1;
-                    const uint32_t dst = hp.extra_base + j + stride - 1;
-                    b->h_mt_tasks[nt++] = MtJumpTask{src, dst, (uint32_t)(b->mt_m + lev), 0};
+                for (uint64_t j = 0; j + stride < hp.n_segs; j += 8 * stride) {
+                    b->h_mt_srcs[ns] = j == 0 ? cur_slot[p] : hp.extra_base + (uint32_t)j - 1;
+                    for (uint64_t d = 1; d < 8 && j + d * stride < hp.n_segs; d++) {
+                        const int slot = mt_poly_slot(db, (d * stride) << b->mt_m, st);
+                        if (slot < 0) { table_full = true; continue; }
+                        b->h_mt_tasks[nt++] = MtJumpTask{(uint32_t)(ns - sstart), hp.extra_base + (uint32_t)(j + d * stride) - 1,
+                                                         (uint32_t)slot, 0};
+                    }
+                    ns++;
                 }
             }
-            if (nt > start) {
-                launches.push_back({start, nt - start});
-                if (b->mt_m + lev > max_poly) max_poly = b->mt_m + lev;
-            }
+            if (nt > start) launches.push_back({start, nt - start, sstart, ns - sstart});
         }
-        if (max_poly >= MAX_POLYS) return fail(PDSAT_ERR_LIMIT, "mt19937 stream offset too large");
+        if (table_full) return fail(PDSAT_ERR_LIMIT, "mt19937 jump polynomial table full");
         if (!launches.empty()) {
-            while (db->n_polys <= max_poly) {
-                const uint32_t* pl = MtJumpPolys::instance().poly(db->n_polys);
-                CU(cudaMemcpyAsync(db->d_polys + (size_t)db->n_polys * 624, pl, sizeof(uint32_t) * 624,
-                                   cudaMemcpyHostToDevice, st));
-                db->n_polys++;
-            }
             CU(cudaMemcpyAsync(b->d_mt_tasks, b->h_mt_tasks, sizeof(MtJumpTask) * nt, cudaMemcpyHostToDevice, st));
-            h2d += (int64_t)(sizeof(MtJumpTask) * nt);
+            CU(cudaMemcpyAsync(b->d_mt_srcs, b->h_mt_srcs, sizeof(uint32_t) * ns, cudaMemcpyHostToDevice, st));
+            h2d += (int64_t)(sizeof(MtJumpTask) * nt + sizeof(uint32_t) * ns);
             for (auto& L : launches) {
-                mt19937_jump_kernel<<<(unsigned)L.cnt * MT_PARTS, MT_JUMP_THREADS, MT_JUMP_SMEM, st>>>(db->d_polys, b->d_mt_states,
-                                                                                             b->d_mt_tasks + L.off);
-                b->n_kernels++;
+                if (L.src_cnt > b->mt_seq_cap) return fail(PDSAT_ERR_LIMIT, "mt19937 jump scratch too small");
+                mt19937_launch_jumps(db->d_polys, b->d_mt_states, b->d_mt_srcs + L.src_off, L.src_cnt,
+                                     b->d_mt_tasks + L.off, L.cnt, b->d_mt_seq, st);
+                b->n_kernels += 2;
             }
         }
         mt19937_bits_kernel<<<(b->n_mt_segs + MT_BITS_WARPS - 1) / MT_BITS_WARPS, MT_BITS_WARPS * 32, 0, st>>>(
@@ -936,10 +958,22 @@ int pdsat_batch_fill(pdsat_batch* b) {
     bd.words = b->d_words;
     bd.stream = b->d_stream;
     bd.block_prefix = b->d_blocks;
-    const int threads = 256;
-    const uint64_t blocks = (b->n_words + threads - 1) / threads;
-    fill_words_kernel<<<(unsigned)blocks, threads, 0, st>>>(bd);
-    b->n_kernels++;
+    bool any_stream = false, any_other = false;
+    for (auto& hp : b->pts) {
+        if (hp.mode == PDSAT_MODE_RANDOM_MT19937 || hp.mode == PDSAT_MODE_EXPLICIT) any_stream = true;
+        else any_other = true;
+    }
+    if (any_other) {  // one thread per word (the words of stream points are left to fill_stream_kernel)
+        const int threads = 256;
+        const uint64_t blocks = (b->n_words + threads - 1) / threads;
+        fill_words_kernel<<<(unsigned)blocks, threads, 0, st>>>(bd);
+        b->n_kernels++;
+    }
+    if (any_stream) {  // one warp per sample group
+        const uint64_t blocks = (b->n_groups + FILL_STREAM_WARPS - 1) / FILL_STREAM_WARPS;
+        fill_stream_kernel<<<(unsigned)blocks, FILL_STREAM_WARPS * 32, 0, st>>>(bd);
+        b->n_kernels++;
+    }
     CU(cudaGetLastError());
     CU(cudaEventRecord(b->ev[1], st));
     b->filled = true;
@@ -1213,6 +1247,7 @@ void pdsat_batch_destroy(pdsat_batch* b) {
     if (b->peer_ranks) pdsat_batch_peer_disconnect(b);
     cudaFree(b->d_peer_own);
     cudaFree(b->d_cta_done);
+    cudaFree(b->d_mt_seq);
     if (b->db && b->db->device >= 0) {
         cudaSetDevice(b->db->device);
         if (b->db->stream) cudaStreamSynchronize(b->db->stream);
@@ -1235,6 +1270,8 @@ void pdsat_batch_destroy(pdsat_batch* b) {
     cudaFree(b->d_mt_states);
     cudaFree(b->d_mt_segs);
     cudaFree(b->d_mt_tasks);
+    cudaFree(b->d_mt_srcs);
+    if (b->h_mt_srcs) cudaFreeHost(b->h_mt_srcs);
     cudaFree(b->d_blocks);
     if (b->h_blocks) cudaFreeHost(b->h_blocks);
     if (b->h_mt_tasks) cudaFreeHost(b->h_mt_tasks);
@@ -1591,62 +1628,76 @@ int pdsat_mt19937_bool_rand(int device, uint32_t seed, uint64_t first, uint64_t 
     if (cudaGetDeviceCount(&cnt) != cudaSuccess || device < 0 || device >= cnt)
         return fail(PDSAT_ERR_CUDA, "no CUDA device (there is no CPU fallback)");
     CU(cudaSetDevice(device));
-    // same machinery as a batch: seed state, jump to round r0 (one in-place jump per set
-    // bit), split the window into 4 segments by tree jumps, emit the bits
+    // same machinery as a batch: seed state, jump to round r0 (one jump per set bit between
+    // the two slots), split the window into 4 segments by three jumps (L, 2L, 3L rounds) that
+    // share the sequence of the first segment, emit the bits
     const uint64_t r0 = first / 624, skip = first - r0 * 624;
     const uint64_t need = (skip + n + 623) / 624;
     int m = 1;
     while ((4ull << m) < need) m++;
+    if (m > 58) return fail(PDSAT_ERR_LIMIT, "mt19937 stream too long");
     const uint64_t L = 1ull << m;
     const int n_segs = 4;
     const uint64_t words = n_segs * (L / 2) * 39;
     std::vector<uint32_t> state(624), hbits(words);
     mt19937_seed(seed, state.data());
     std::vector<MtJumpTask> tasks;
-    std::vector<std::pair<size_t, size_t>> launches;
-    int max_poly = -1;
+    std::vector<uint32_t> srcs;
+    std::vector<uint64_t> poly_rounds;  // device slot i holds x^(624 * poly_rounds[i])
+    struct Launch { size_t off, cnt, src_off, src_cnt; };
+    std::vector<Launch> launches;
     uint32_t cur = 0;  // slots 0/1: ping-pong pair, slots 2..4: segments 1..3
     for (int t = 0; t < 64; t++)
         if ((r0 >> t) & 1ull) {
-            launches.push_back({tasks.size(), 1});
-            tasks.push_back(MtJumpTask{cur, cur ^ 1u, (uint32_t)t, 0});
+            launches.push_back({tasks.size(), 1, srcs.size(), 1});
+            tasks.push_back(MtJumpTask{0, cur ^ 1u, (uint32_t)poly_rounds.size(), 0});
+            srcs.push_back(cur);
+            poly_rounds.push_back(1ull << t);
             cur ^= 1u;
-            max_poly = t;
         }
-    launches.push_back({tasks.size(), 1});
-    tasks.push_back(MtJumpTask{cur, 3, (uint32_t)(m + 1), 0});
-    launches.push_back({tasks.size(), 2});
-    tasks.push_back(MtJumpTask{cur, 2, (uint32_t)m, 0});
-    tasks.push_back(MtJumpTask{3, 4, (uint32_t)m, 0});
-    if (m + 1 > max_poly) max_poly = m + 1;
-    if (max_poly >= MAX_POLYS) return fail(PDSAT_ERR_LIMIT, "mt19937 stream offset too large");
+    launches.push_back({tasks.size(), 3, srcs.size(), 1});
+    srcs.push_back(cur);
+    for (uint32_t d = 1; d <= 3; d++) {
+        tasks.push_back(MtJumpTask{0, d + 1, (uint32_t)poly_rounds.size(), 0});
+        poly_rounds.push_back(d * L);
+    }
     std::vector<MtSegment> segs(n_segs);
     for (int j = 0; j < n_segs; j++) segs[j] = MtSegment{(uint64_t)j * (L / 2) * 39, L, j == 0 ? cur : (uint32_t)(j + 1), 0};
-    uint32_t *d_state = nullptr, *d_out = nullptr, *d_polys = nullptr;
+    uint32_t *d_state = nullptr, *d_out = nullptr, *d_polys = nullptr, *d_srcs = nullptr;
     MtSegment* d_seg = nullptr;
     MtJumpTask* d_tasks = nullptr;
     CU(cudaMalloc(&d_state, 624 * 4 * MT_PARTS * 5));
     CU(cudaMemset(d_state, 0, 624 * 4 * MT_PARTS * 5));
     CU(cudaMalloc(&d_seg, sizeof(MtSegment) * n_segs));
     CU(cudaMalloc(&d_out, words * 4));
-    CU(cudaMalloc(&d_polys, (size_t)(max_poly + 1) * 624 * 4));
+    CU(cudaMalloc(&d_polys, poly_rounds.size() * 624 * 4));
     CU(cudaMalloc(&d_tasks, sizeof(MtJumpTask) * tasks.size()));
-    for (int t = 0; t <= max_poly; t++)
-        CU(cudaMemcpy(d_polys + (size_t)t * 624, MtJumpPolys::instance().poly(t), 624 * 4, cudaMemcpyHostToDevice));
+    CU(cudaMalloc(&d_srcs, sizeof(uint32_t) * srcs.size()));
+    for (size_t i = 0; i < poly_rounds.size(); i++) {
+        const uint64_t r = poly_rounds[i];
+        const uint32_t* pl = __builtin_popcountll(r) == 1 ? MtJumpPolys::instance().poly(__builtin_ctzll(r))
+                                                          : MtJumpPolys::instance().poly_for_rounds(r);
+        CU(cudaMemcpy(d_polys + i * 624, pl, 624 * 4, cudaMemcpyHostToDevice));
+    }
     CU(cudaMemcpy(d_state, state.data(), 624 * 4, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(d_seg, segs.data(), sizeof(MtSegment) * n_segs, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(d_tasks, tasks.data(), sizeof(MtJumpTask) * tasks.size(), cudaMemcpyHostToDevice));
-    CU(cudaFuncSetAttribute(mt19937_jump_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MT_JUMP_SMEM));
+    CU(cudaMemcpy(d_srcs, srcs.data(), sizeof(uint32_t) * srcs.size(), cudaMemcpyHostToDevice));
+    uint32_t* d_seq = nullptr;
+    CU(cudaMalloc(&d_seq, sizeof(uint32_t) * MT_SEQ_WORDS));
+    CU(cudaFuncSetAttribute(mt19937_seq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MT_SEQ_SMEM));
     for (auto& l : launches)
-        mt19937_jump_kernel<<<(unsigned)l.second * MT_PARTS, MT_JUMP_THREADS, MT_JUMP_SMEM>>>(d_polys, d_state, d_tasks + l.first);
+        mt19937_launch_jumps(d_polys, d_state, d_srcs + l.src_off, l.src_cnt, d_tasks + l.off, l.cnt, d_seq, 0);
     mt19937_bits_kernel<<<(n_segs + MT_BITS_WARPS - 1) / MT_BITS_WARPS, MT_BITS_WARPS * 32>>>(d_state, d_seg, n_segs, (uint32_t)L, d_out);
     CU(cudaGetLastError());
     CU(cudaMemcpy(hbits.data(), d_out, words * 4, cudaMemcpyDeviceToHost));
     cudaFree(d_state);
+    cudaFree(d_seq);
     cudaFree(d_seg);
     cudaFree(d_out);
     cudaFree(d_polys);
     cudaFree(d_tasks);
+    cudaFree(d_srcs);
     for (uint64_t i = 0; i < n; i++) {
         uint64_t d = skip + i;
         out[i] = (hbits[d >> 5] >> (d & 31)) & 1u;
