@@ -186,6 +186,10 @@ int pdsat_batch_propagate(pdsat_batch* b);
 int pdsat_batch_sync(pdsat_batch* b);
 /* device time of the last fill / propagate on this batch, CUDA events on the launch stream */
 int pdsat_batch_last_ms(pdsat_batch* b, float* fill_ms, float* propagate_ms);
+/* Stage timing on (default) / off.  The four event records per step are device-side work on the
+ * launch stream (about 1 us each): a caller that launches steps back to back and never asks for
+ * pdsat_batch_last_ms turns them off.  With timing off pdsat_batch_last_ms reports 0. */
+int pdsat_batch_set_timing(pdsat_batch* b, int32_t on);
 int pdsat_batch_launch_count(pdsat_batch* b, int64_t* n_kernels);
 /* host->device bytes copied by the last pdsat_batch_fill (descriptors, generator seeds, jump plan,
  * explicit values) */

@@ -25,7 +25,7 @@ EXPORTS = [
     "pdsat_last_error", "pdsat_device_count", "pdsat_upload_cnf", "pdsat_set_fixed_assumptions",
     "pdsat_db_get_info", "pdsat_db_base_assignment", "pdsat_set_stream", "pdsat_destroy",
     "pdsat_batch_create", "pdsat_batch_reseed", "pdsat_batch_fill", "pdsat_batch_propagate",
-    "pdsat_batch_sync", "pdsat_batch_last_ms", "pdsat_batch_launch_count", "pdsat_batch_cost_device_ptr",
+    "pdsat_batch_sync", "pdsat_batch_last_ms", "pdsat_batch_set_timing", "pdsat_batch_launch_count", "pdsat_batch_cost_device_ptr",
     "pdsat_batch_set_cost_buffer", "pdsat_batch_costs", "pdsat_batch_flags", "pdsat_batch_trail",
     "pdsat_batch_assign", "pdsat_batch_models", "pdsat_batch_destroy", "pdsat_eval_batch",
     "pdsat_mt19937_bool_rand", "pdsat_batch_peer_export", "pdsat_batch_peer_connect",
@@ -117,6 +117,7 @@ def lib():
     L.pdsat_batch_propagate.argtypes = [C.c_void_p]
     L.pdsat_batch_sync.argtypes = [C.c_void_p]
     L.pdsat_batch_last_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    L.pdsat_batch_set_timing.argtypes = [C.c_void_p, C.c_int32]
     L.pdsat_batch_launch_count.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
     L.pdsat_batch_cost_device_ptr.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
     L.pdsat_batch_set_cost_buffer.argtypes = [C.c_void_p, C.c_void_p]
@@ -350,6 +351,10 @@ class Batch:
         f, p = C.c_float(0), C.c_float(0)
         _check(lib().pdsat_batch_last_ms(self.h, C.byref(f), C.byref(p)))
         return f.value, p.value
+
+    def set_timing(self, on: bool) -> None:
+        """stage timing (four event records per step on the launch stream) on / off"""
+        _check(lib().pdsat_batch_set_timing(self.h, 1 if on else 0))
 
     def launch_count(self) -> int:
         n = C.c_int64(0)

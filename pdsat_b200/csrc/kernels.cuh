@@ -108,6 +108,11 @@ struct BatchDev {
     unsigned long long* acc;    // n_points * 8: scratch the warps add into; zero between launches (the
                                 // last CTA publishes it into `cost` and clears it: no memset per step)
     unsigned int* cta_done;     // ticket counter (last-CTA detection)
+    unsigned long long* zero_next;  // direct path (no peers, library-owned buffers): acc IS the output
+                                    // of this launch, CTA 0 clears zero_next (= the next launch's) and
+                                    // nobody publishes; nullptr: ticket path
+    PointDev p0;                // point 0 again, in the kernel parameters: the first tile of a one-point
+                                // batch is requested without a global load in front of it
     uint64_t* conflict_bits;    // per global group (optional)
     uint64_t* full_bits;        // per global group (optional)
     uint32_t* trail;            // per global group * 64 (optional)
@@ -894,6 +899,20 @@ static constexpr int MAX_COUNT_BITS = 15;
 
 // Per-warp accumulators of the current point: 8 x u64 in the warp's shared memory (lane 0 adds;
 // sixteen registers less in the propagation loop), flushed with <= 8 atomicAdds per point change.
+#ifdef PDSAT_TIMELINE  // experiments only: per-CTA timestamps of the phases of bcp_kernel
+__device__ unsigned long long g_timeline[148 * 8];
+__device__ __forceinline__ void tl_mark(int i) {
+    if (threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+        g_timeline[blockIdx.x * 8 + i] = t;
+    }
+}
+#define TL(i) tl_mark(i)
+#else
+#define TL(i)
+#endif
+
 enum { ACC_N = 0, ACC_CONFLICT, ACC_FULL, ACC_SUM, ACC_SUMSQ, ACC_IMPL, ACC_POPS, ACC_TOUCHED };
 
 __device__ __forceinline__ void flush_acc(uint64_t* a, int point, unsigned long long* cost, int lane) {
@@ -995,6 +1014,7 @@ __device__ __forceinline__ void bcp_body(const DbDev& db, const BatchDev& b, int
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int wpc = blockDim.x >> 5;
+    TL(0);
 
     // ---- index blob (occurrence offsets, gate lists, gate records): one bulk copy per CTA into
     // shared memory when it fits, otherwise read from global / L2
@@ -1076,14 +1096,22 @@ __device__ __forceinline__ void bcp_body(const DbDev& db, const BatchDev& b, int
                 const int pp = find_point_run(b.points, b.n_points, pf_r);
                 const PointDev* pt = &b.points[pp];
                 pf_run_end = pp + 1 < b.n_points ? b.points[pp + 1].run_start : b.n_runs;
-                pf_T = pt->tile;
-                const uint64_t groups = (pp + 1 < b.n_points ? b.points[pp + 1].group_start : b.n_groups) - pt->group_start;
-                const uint64_t g_rel = (pf_r - pt->run_start) * pf_T;  // first group of the run inside its point
-                pf_ptr = b.words + pt->word_off + g_rel * pt->kp;
+                uint64_t pt_group_start, pt_run_start, pt_word_off;
+                uint32_t pt_kp;
+                if (pp == 0) {  // from the kernel parameters
+                    pf_T = b.p0.tile, pt_group_start = b.p0.group_start, pt_run_start = b.p0.run_start;
+                    pt_word_off = b.p0.word_off, pt_kp = b.p0.kp;
+                } else {
+                    pf_T = pt->tile, pt_group_start = pt->group_start, pt_run_start = pt->run_start;
+                    pt_word_off = pt->word_off, pt_kp = pt->kp;
+                }
+                const uint64_t groups = (pp + 1 < b.n_points ? b.points[pp + 1].group_start : b.n_groups) - pt_group_start;
+                const uint64_t g_rel = (pf_r - pt_run_start) * pf_T;  // first group of the run inside its point
+                pf_ptr = b.words + pt_word_off + g_rel * pt_kp;
                 pf_left = (int64_t)(groups - g_rel);
                 pf_gstep = (int64_t)(stride * pf_T);
-                pf_step = stride * pf_T * pt->kp;
-                pf_gbytes = pt->kp * 8u;
+                pf_step = stride * pf_T * pt_kp;
+                pf_gbytes = pt_kp * 8u;
             }
             const uint32_t bytes = (pf_left >= (int64_t)pf_T ? pf_T : (uint32_t)pf_left) * pf_gbytes;
             mbar_expect_tx_s(bar_s + pf_stage * 8u, bytes);
@@ -1097,32 +1125,40 @@ __device__ __forceinline__ void bcp_body(const DbDev& db, const BatchDev& b, int
     if (lane == 0)
         for (int s = 0; s < stages; s++) prefetch_one();
 
-    if (db.blob_in_smem) {
-        __syncthreads();  // the barrier init is visible to everybody
-        mbar_wait(blob_bar, 0);
-    }
+    // the index blob is waited for by the first group that propagates (streaming points never
+    // look at it) or, at the latest, before the CTA leaves
+    bool blob_ready = !db.blob_in_smem;
+    // CTA accumulator of the final flush: the first warp to finish names the point
+    __shared__ unsigned long long s_acc[8];
+    __shared__ int s_point;
+    if (threadIdx.x < 8) s_acc[threadIdx.x] = 0;
+    if (threadIdx.x == 8) s_point = -1;
+    if (b.zero_next != nullptr && blockIdx.x == 0)  // direct path: clear the accumulators of the next launch
+        for (int i = threadIdx.x; i < b.n_points * 8; i += blockDim.x) b.zero_next[i] = 0;
+    __syncthreads();  // also: the blob barrier init is visible to everybody
+    TL(1);
 
     // current point, cached in registers (a warp usually stays inside one point for many groups)
     int p = -1, p_prev = -1;
     uint64_t P_start = 0, P_end = 0, P_n_samples = 0, P_run_start = 0, P_run_end = 0;
-    uint32_t k = 0, P_var_off = 0, P_n_assumed = 0, P_cand_off = 0, P_cand_cnt = 0, P_code0 = 0, P_flags = 0;
+    uint32_t k = 0, P_var_off = 0, P_n_assumed = 0, P_cand_off = 0, P_cand_cnt = 0, P_code0 = 0, P_flags = 0, P_tile = 1;
     int stage = 0;
     uint32_t phase = 0;
     for (uint64_t run = r_first; run < b.n_runs; run += stride) {
         if (p < 0 || run >= P_run_end) {
             p = find_point_run(b.points, b.n_points, run);
-            const PointDev* pt = &b.points[p];
-            P_start = pt->group_start;
             P_end = p + 1 < b.n_points ? b.points[p + 1].group_start : b.n_groups;
-            P_run_start = pt->run_start;
             P_run_end = p + 1 < b.n_points ? b.points[p + 1].run_start : b.n_runs;
-            P_n_samples = pt->n_samples;
-            k = pt->k;
-            P_var_off = pt->var_off;
-            P_n_assumed = pt->n_assumed_live;
-            P_cand_off = pt->cand_off;
-            P_cand_cnt = pt->cand_cnt;
-            P_flags = pt->flags;
+            if (p == 0) {  // from the kernel parameters
+                P_start = b.p0.group_start, P_run_start = b.p0.run_start, P_n_samples = b.p0.n_samples;
+                k = b.p0.k, P_var_off = b.p0.var_off, P_n_assumed = b.p0.n_assumed_live;
+                P_cand_off = b.p0.cand_off, P_cand_cnt = b.p0.cand_cnt, P_flags = b.p0.flags, P_tile = b.p0.tile;
+            } else {
+                const PointDev* pt = &b.points[p];
+                P_start = pt->group_start, P_run_start = pt->run_start, P_n_samples = pt->n_samples;
+                k = pt->k, P_var_off = pt->var_off, P_n_assumed = pt->n_assumed_live;
+                P_cand_off = pt->cand_off, P_cand_cnt = pt->cand_cnt, P_flags = pt->flags, P_tile = pt->tile;
+            }
             P_code0 = lane < (int)k ? b.setcode[P_var_off + lane] : 0u;
             flush_acc(accs, p_prev, b.acc, lane);
             p_prev = p;
@@ -1139,11 +1175,14 @@ __device__ __forceinline__ void bcp_body(const DbDev& db, const BatchDev& b, int
             const uint64_t g_last = P_end - 1;  // the only group of the point that can be ragged
             const uint32_t n_tail = (uint32_t)(P_n_samples - (g_last - P_start) * 64);
             const bool want_out = b.conflict_bits != nullptr || b.trail != nullptr;
-            const uint32_t T = b.points[p].tile;
+            const uint32_t T = P_tile;
             uint32_t cnt = 0;
             while (true) {
                 mbar_wait_s(bar_s + (uint32_t)stage * 8u, phase);  // the tile has landed (and is not needed)
                 __syncwarp();
+#ifdef PDSAT_TIMELINE
+                if (cnt == 0) TL(2);
+#endif
                 if (lane == 0) prefetch_one();
                 stage = stage + 1 == stages ? 0 : stage + 1;
                 phase ^= (stage == 0);
@@ -1181,6 +1220,10 @@ __device__ __forceinline__ void bcp_body(const DbDev& db, const BatchDev& b, int
         }
 
         // a point in which BCP can start has runs of one group
+        if (!blob_ready) {
+            mbar_wait(blob_bar, 0);
+            blob_ready = true;
+        }
         const uint64_t gi = run - P_run_start;
         const uint64_t g = P_start + gi;
         const uint64_t s0 = gi * 64;
@@ -1487,15 +1530,47 @@ __device__ __forceinline__ void bcp_body(const DbDev& db, const BatchDev& b, int
             b.full_bits[g] = full64;
         }
     }
-    flush_acc(accs, p_prev, b.acc, lane);
+    TL(3);
+    if (!blob_ready) mbar_wait(blob_bar, 0);  // no bulk copy may be in flight when the CTA exits
+    TL(4);
 
-    // ---- the last CTA publishes the accumulators: alone, or after the exchange with the peers
+    // ---- final flush: the warps that end in the same point as the first warp to finish (usually
+    // all of them) add into the CTA accumulator - 8 global atomics per CTA instead of 8 per warp on
+    // the same two cache lines (a serial tail of several microseconds on a 20 us launch)
+    __shared__ unsigned int s_ticket;
     {
-        __shared__ unsigned int s_ticket;
-        __threadfence();
+        int cta_point = -1;
+        if (p_prev >= 0) {
+            if (lane == 0) {
+                const int old = atomicCAS(&s_point, -1, p_prev);
+                cta_point = old < 0 ? p_prev : old;
+            }
+            cta_point = __shfl_sync(0xffffffffu, cta_point, 0);
+            if (cta_point == p_prev) {
+                if (lane < 8) {
+                    const unsigned long long v = accs[lane];
+                    if (v) atomicAdd(&s_acc[lane], v);
+                }
+            } else {
+                flush_acc(accs, p_prev, b.acc, lane);
+                __threadfence();
+            }
+        }
         __syncthreads();
-        if (threadIdx.x == 0) s_ticket = atomicAdd(b.cta_done, 1u);
+        TL(5);
+        if (warp != 0) {
+            if (b.zero_next != nullptr) return;  // direct path: nothing to publish
+        } else {
+            if (lane < 8 && s_point >= 0 && s_acc[lane]) atomicAdd(&b.acc[(size_t)s_point * 8 + lane], s_acc[lane]);
+            if (b.zero_next != nullptr) return;
+            // ---- ticket path: the last CTA publishes the accumulators, alone or after the exchange
+            // with the peers
+            __threadfence();
+            __syncwarp();
+            if (lane == 0) s_ticket = atomicAdd(b.cta_done, 1u);
+        }
         __syncthreads();
+        TL(6);
         if (s_ticket != gridDim.x - 1) return;
         __threadfence();
         const int nw = b.n_points * 8;
@@ -1537,6 +1612,7 @@ __device__ __forceinline__ void bcp_body(const DbDev& db, const BatchDev& b, int
             }
         }
         if (threadIdx.x == 0) *b.cta_done = 0;
+        TL(7);
     }
 }
 

@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
 #include <map>
 #include <string>
 #include <vector>
@@ -111,8 +112,20 @@ struct pdsat_batch {
     uint4* d_cand = nullptr;
     uint64_t* d_words = nullptr;
     uint32_t* d_stream = nullptr;
-    unsigned long long* d_cost = nullptr;
+    unsigned long long* d_cost = nullptr;   // published accumulators (ticket path), or buffer 0 of the direct path
+    unsigned long long* d_cost2 = nullptr;  // buffer 1 of the direct path
     unsigned long long* d_cost_ext = nullptr;
+    // Direct path (no peers, no caller-owned cost buffer): the CTAs add straight into
+    // d_cost / d_cost2 alternately and CTA 0 clears the other one for the next launch - no ticket,
+    // no publishing pass at the end of the kernel.
+    bool timing = true, fill_timed = false, propagate_timed = false;  // pdsat_batch_set_timing
+    int cost_cur = 0;          // buffer the last direct launch wrote
+    bool last_direct = false;  // the last launch took the direct path
+    bool no_direct = false;    // the caller holds a device pointer to the costs: keep it stable
+    unsigned long long* cost_ptr() const {
+        if (last_direct) return cost_cur ? d_cost2 : d_cost;
+        return d_cost_ext ? d_cost_ext : d_cost;
+    }
     unsigned long long* d_acc = nullptr;  // scratch accumulators, zero between launches
     uint64_t* d_conflict = nullptr;
     uint64_t* d_full = nullptr;
@@ -148,6 +161,7 @@ struct pdsat_batch {
     unsigned long long* d_peer_own = nullptr;          // this rank's IPC-exported buffer
     unsigned long long* peer_ptr[MAX_PEERS] = {};      // every rank's buffer as mapped here
     unsigned int* d_cta_done = nullptr;
+    bool counted_mt = false;       // counted in g_mt_batches
     uint32_t* d_mt_seq = nullptr;  // sequences of one level of jump-aheads (mt19937_seq_kernel)
     size_t mt_seq_cap = 0;
     int peer_ranks = 0, peer_me = 0;
@@ -212,7 +226,9 @@ static LaunchShape launch_shape_bits(const pdsat_db* db, uint32_t stage_bytes, i
     // 3 KB of tiles in flight per warp (x 12..16 warps x 148 SMs covers the HBM latency x
     // bandwidth product); at least double buffering for the large sets
     L.stage_bytes = (int)stage_bytes;
-    int st = 3072 / (L.stage_bytes > 0 ? L.stage_bytes : 16);
+    int ring_budget = 3072;
+    if (const char* e = getenv("PDSAT_RING_BYTES")) ring_budget = atoi(e) > 0 ? atoi(e) : ring_budget;
+    int st = ring_budget / (L.stage_bytes > 0 ? L.stage_bytes : 16);
     L.stages = st < 2 ? 2 : (st > 8 ? 8 : st);
     const int ring = ((L.stages + 1) & ~1) * 8 + L.stages * L.stage_bytes;
     const int pb = plane_bits / 8;
@@ -454,10 +470,18 @@ static void mt_plan(HostPoint& hp) {
     hp.mt_rounds = (623 + hp.n_samples * k + 623) / 624;
 }
 
-static int mt_target_segments() {
+// Segments (= generator warps) a batch cuts its mt19937 streams into.  More segments keep more
+// schedulers busy in mt19937_bits_kernel but every segment costs one jump-ahead: a batch that is
+// alone on its device gets ~4 per SM; when several batches with mt19937 points are alive on the
+// device (a pipeline of handles, several search workers) their generator kernels overlap on
+// the SMs and half as many segments per batch is the better trade (measured: profiles/README.md).
+static std::atomic<int> g_mt_batches[64];
+static int mt_target_segments(int device) {
     const char* e = getenv("PDSAT_MT_SEGMENTS");
     int t = e ? atoi(e) : 0;
-    return t > 0 ? t : 1184;  // 2 warps per scheduler on a 148-SM part
+    if (t > 0) return t;
+    const int alive = device >= 0 && device < 64 ? g_mt_batches[device].load() : 1;
+    return alive >= 2 ? 296 : 592;
 }
 
 int pdsat_batch_create(pdsat_db* db, int32_t n_points, const pdsat_point* points, uint32_t out_flags,
@@ -600,7 +624,12 @@ int pdsat_batch_create(pdsat_db* db, int32_t n_points, const pdsat_point* points
         uint64_t total_rounds = 0;
         for (auto& hp : b->pts)
             if (hp.mode == PDSAT_MODE_RANDOM_MT19937) total_rounds += hp.mt_rounds;
-        const uint64_t per_seg = (total_rounds + mt_target_segments() - 1) / mt_target_segments();
+        if (db->device >= 0 && db->device < 64) {
+            g_mt_batches[db->device]++;
+            b->counted_mt = true;
+        }
+        const int target = mt_target_segments(db->device);
+        const uint64_t per_seg = (total_rounds + target - 1) / target;
         int m = 1;
         while ((1ull << m) < per_seg) m++;
         b->mt_m = m;
@@ -660,6 +689,8 @@ int pdsat_batch_create(pdsat_db* db, int32_t n_points, const pdsat_point* points
     CUB(cudaMalloc(&b->d_acc, sizeof(unsigned long long) * PDSAT_COST_WORDS * n_points));
     CUB(cudaMemset(b->d_acc, 0, sizeof(unsigned long long) * PDSAT_COST_WORDS * n_points));
     CUB(cudaMemset(b->d_cost, 0, sizeof(unsigned long long) * PDSAT_COST_WORDS * n_points));
+    CUB(cudaMalloc(&b->d_cost2, sizeof(unsigned long long) * PDSAT_COST_WORDS * n_points));
+    CUB(cudaMemset(b->d_cost2, 0, sizeof(unsigned long long) * PDSAT_COST_WORDS * n_points));
     CUB(cudaMalloc(&b->d_cta_done, sizeof(unsigned int)));
     CUB(cudaMemset(b->d_cta_done, 0, sizeof(unsigned int)));
     CUB(cudaMalloc(&b->d_model_count, sizeof(unsigned long long)));
@@ -826,7 +857,7 @@ int pdsat_batch_fill(pdsat_batch* b) {
     CU(cudaSetDevice(db->device));
     staging_wait(b);  // the previous fill may still be reading the pinned staging buffers
     cudaStream_t st = db->stream;
-    CU(cudaEventRecord(b->ev[0], st));
+    if (b->timing) CU(cudaEventRecord(b->ev[0], st));
     {
         uint64_t runs = 0;  // first run of every point (a run = tile_groups consecutive groups, one bulk copy)
         for (size_t p = 0; p < b->pts.size(); p++) {
@@ -975,7 +1006,8 @@ int pdsat_batch_fill(pdsat_batch* b) {
         b->n_kernels++;
     }
     CU(cudaGetLastError());
-    CU(cudaEventRecord(b->ev[1], st));
+    if (b->timing) CU(cudaEventRecord(b->ev[1], st));
+    b->fill_timed = b->timing;
     b->filled = true;
     b->h2d_bytes_last_fill = h2d;
     return PDSAT_OK;
@@ -988,8 +1020,17 @@ int pdsat_batch_propagate(pdsat_batch* b) {
     pdsat_db* db = b->db;
     CU(cudaSetDevice(db->device));
     cudaStream_t st = db->stream;
-    unsigned long long* cost = b->d_cost_ext ? b->d_cost_ext : b->d_cost;
-    CU(cudaEventRecord(b->ev[2], st));
+    const bool direct = b->peer_ranks == 0 && !b->d_cost_ext && !b->no_direct;
+    const size_t cost_bytes = sizeof(unsigned long long) * PDSAT_COST_WORDS * b->pts.size();
+    if (direct != b->last_direct) {  // path change (rare): both conventions start from zeroed buffers
+        CU(cudaMemsetAsync(b->d_cost, 0, cost_bytes, st));
+        CU(cudaMemsetAsync(b->d_cost2, 0, cost_bytes, st));
+        CU(cudaMemsetAsync(b->d_acc, 0, cost_bytes, st));
+    }
+    if (direct) b->cost_cur ^= 1;
+    b->last_direct = direct;
+    unsigned long long* cost = b->cost_ptr();
+    if (b->timing) CU(cudaEventRecord(b->ev[2], st));
     // no memset of the accumulators: the kernel's last CTA publishes the scratch sums and clears them
     if (b->max_models > 0) CU(cudaMemsetAsync(b->d_model_count, 0, sizeof(unsigned long long), st));
     BatchDev bd{};
@@ -1002,8 +1043,10 @@ int pdsat_batch_propagate(pdsat_batch* b) {
     bd.words = b->d_words;
     bd.stream = b->d_stream;
     bd.cost = cost;
-    bd.acc = b->d_acc;
+    bd.acc = direct ? cost : b->d_acc;
+    bd.zero_next = direct ? (b->cost_cur ? b->d_cost : b->d_cost2) : nullptr;
     bd.cta_done = b->d_cta_done;
+    bd.p0 = b->h_points[0];
     bd.conflict_bits = b->d_conflict;
     bd.full_bits = b->d_full;
     bd.trail = b->d_trail;
@@ -1043,7 +1086,8 @@ int pdsat_batch_propagate(pdsat_batch* b) {
     b->n_kernels++;
     if (b->peer_ranks > 0) b->peer_step++;  // the exchange happens inside the kernel (its last CTA)
     CU(cudaGetLastError());
-    CU(cudaEventRecord(b->ev[3], st));
+    if (b->timing) CU(cudaEventRecord(b->ev[3], st));
+    b->propagate_timed = b->timing;
     b->propagated = true;
     return PDSAT_OK;
 }
@@ -1059,12 +1103,18 @@ int pdsat_batch_last_ms(pdsat_batch* b, float* fill_ms, float* propagate_ms) {
     CU(cudaStreamSynchronize(b->db->stream));
     if (fill_ms) {
         *fill_ms = 0;
-        if (b->filled) CU(cudaEventElapsedTime(fill_ms, b->ev[0], b->ev[1]));
+        if (b->filled && b->fill_timed) CU(cudaEventElapsedTime(fill_ms, b->ev[0], b->ev[1]));
     }
     if (propagate_ms) {
         *propagate_ms = 0;
-        if (b->propagated) CU(cudaEventElapsedTime(propagate_ms, b->ev[2], b->ev[3]));
+        if (b->propagated && b->propagate_timed) CU(cudaEventElapsedTime(propagate_ms, b->ev[2], b->ev[3]));
     }
+    return PDSAT_OK;
+}
+
+int pdsat_batch_set_timing(pdsat_batch* b, int32_t on) {
+    if (!b) return fail(PDSAT_ERR_ARG, "pdsat_batch_set_timing: null batch");
+    b->timing = on != 0;
     return PDSAT_OK;
 }
 
@@ -1082,6 +1132,7 @@ int pdsat_batch_h2d_bytes(pdsat_batch* b, int64_t* bytes) {
 
 int pdsat_batch_cost_device_ptr(pdsat_batch* b, void** dptr) {
     if (!b || !dptr) return fail(PDSAT_ERR_ARG, "pdsat_batch_cost_device_ptr: bad argument");
+    b->no_direct = true;  // the pointer stays valid for every later launch
     *dptr = b->d_cost_ext ? b->d_cost_ext : b->d_cost;
     return PDSAT_OK;
 }
@@ -1096,7 +1147,7 @@ int pdsat_batch_costs(pdsat_batch* b, pdsat_cost* out) {
     if (!b || !out) return fail(PDSAT_ERR_ARG, "pdsat_batch_costs: bad argument");
     if (!b->propagated) return fail(PDSAT_ERR_ARG, "pdsat_batch_costs: batch not propagated");
     static_assert(sizeof(pdsat_cost) == 8 * PDSAT_COST_WORDS, "pdsat_cost layout");
-    unsigned long long* cost = b->d_cost_ext ? b->d_cost_ext : b->d_cost;
+    unsigned long long* cost = b->cost_ptr();
     CU(cudaMemcpyAsync(out, cost, sizeof(pdsat_cost) * b->pts.size(), cudaMemcpyDeviceToHost, b->db->stream));
     CU(cudaStreamSynchronize(b->db->stream));
     return PDSAT_OK;
@@ -1161,7 +1212,7 @@ int pdsat_batch_models(pdsat_batch* b, int64_t* n_found, int32_t* point_of, uint
         CU(cudaMemcpy(&cnt, b->d_model_count, sizeof(cnt), cudaMemcpyDeviceToHost));
     } else {  // nothing is stored: the count is the sum of the points' n_full
         std::vector<pdsat_cost> c(b->pts.size());
-        unsigned long long* cost = b->d_cost_ext ? b->d_cost_ext : b->d_cost;
+        unsigned long long* cost = b->cost_ptr();
         CU(cudaMemcpy(c.data(), cost, sizeof(pdsat_cost) * c.size(), cudaMemcpyDeviceToHost));
         for (auto& x : c) cnt += x.n_full;
     }
@@ -1244,6 +1295,7 @@ int pdsat_batch_peer_disconnect(pdsat_batch* b) {
 
 void pdsat_batch_destroy(pdsat_batch* b) {
     if (!b) return;
+    if (b->counted_mt) g_mt_batches[b->db->device]--;
     if (b->peer_ranks) pdsat_batch_peer_disconnect(b);
     cudaFree(b->d_peer_own);
     cudaFree(b->d_cta_done);
@@ -1258,6 +1310,7 @@ void pdsat_batch_destroy(pdsat_batch* b) {
     cudaFree(b->d_words);
     cudaFree(b->d_stream);
     cudaFree(b->d_cost);
+    cudaFree(b->d_cost2);
     cudaFree(b->d_acc);
     cudaFree(b->d_conflict);
     cudaFree(b->d_full);
@@ -1704,5 +1757,13 @@ int pdsat_mt19937_bool_rand(int device, uint32_t seed, uint64_t first, uint64_t 
     }
     return PDSAT_OK;
 }
+
+#ifdef PDSAT_TIMELINE
+int pdsat_debug_timeline(unsigned long long* out) {
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpyFromSymbol(out, g_timeline, sizeof(unsigned long long) * 148 * 8));
+    return PDSAT_OK;
+}
+#endif
 
 }  // extern "C"
