@@ -668,7 +668,7 @@ def run_ours(args):
     # reads its own 64-byte result back, the read of step s waits only for step s.  The stages of a
     # step (jump tree, bit generator, transpose, BCP) are latency-bound kernels with small grids:
     # steps that overlap fill each other's idle issue slots.
-    depth = max(1, args.pipeline if dist is None else min(args.pipeline, 2))
+    depth = max(1, args.pipeline if dist is None else min(args.pipeline, 4))
     lanes = []
     for d in range(depth):
         if d == 0:
@@ -960,7 +960,7 @@ def main():
     ap.add_argument("--cascade", type=lambda v: [int(x) for x in v.split(",") if x], default=[86, 90, 100, 120, 177],
                     help="set sizes (bivium_Ending2 prefixes) of the timed + parity-checked cascade legs")
     ap.add_argument("--cascade-samples", type=int, default=1_000_000)
-    ap.add_argument("--pipeline", type=int, default=8, help="steps in flight in the e2e measurement (1 GPU; 2 when N > 1)")
+    ap.add_argument("--pipeline", type=int, default=8, help="steps in flight in the e2e measurement (1 GPU; at most 4 when N > 1)")
     ap.add_argument("--tabu-samples", type=int, default=1_000_000, help="samples per point of the tabu-step leg")
     ap.add_argument("--odls-samples", type=int, default=1_000_000)
     ap.add_argument("--odls-check", type=int, default=20_000, help="ODLS samples compared with the reference BCP")

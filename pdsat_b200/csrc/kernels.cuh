@@ -92,7 +92,12 @@ struct PeerDev {
     int32_t parity;
     int32_t n_words;                        // accumulators = n_points * 8
     uint32_t tag;                           // step number + 1 (never 0)
+    unsigned int* timed_out;                // set when a peer's packets did not arrive within PEER_TIMEOUT_NS
 };
+// a rank that never launches its step (crashed, or the caller broke the "same calls on every
+// rank" rule) must not leave the others spinning for ever: the wait gives up and the host
+// reports an error from pdsat_batch_costs
+static constexpr unsigned long long PEER_TIMEOUT_NS = 20ull * 1000 * 1000 * 1000;
 
 struct BatchDev {
     const PointDev* points;
@@ -483,24 +488,24 @@ struct MtWarp {
             carry = w >> 16;
         }
     }
-    // The 20 chunks of a round go in three groups (0-6, 7-13, 14-19).  Inside a group no chunk
-    // needs another chunk's NEW words (mt[k+397] is >= 227 words away), so all shuffles of the
-    // group are issued first and their latencies overlap; the group's updates follow.
+    // A chunk's neighbours are 1 and 397 words ahead (= 227 behind, new): chunk c needs the NEW
+    // words of chunks c-8 and c-7 and the OLD words of chunk c+1.  So the round is a software
+    // pipeline of distance 7: right after chunk j is updated the shuffles of chunk j+7 are issued,
+    // and their results are consumed seven updates later - the shuffle latency is hidden by
+    // independent work even with one warp per scheduler.
     template <int ODD>
     __device__ __forceinline__ void round() {
-        uint32_t b0, b1, b2, b3, b4, b5, b6, m0, m1, m2, m3, m4, m5, m6;
-        gather<0>(b0, m0); gather<1>(b1, m1); gather<2>(b2, m2); gather<3>(b3, m3);
-        gather<4>(b4, m4); gather<5>(b5, m5); gather<6>(b6, m6);
-        update<0, ODD>(b0, m0); update<1, ODD>(b1, m1); update<2, ODD>(b2, m2); update<3, ODD>(b3, m3);
-        update<4, ODD>(b4, m4); update<5, ODD>(b5, m5); update<6, ODD>(b6, m6);
-        gather<7>(b0, m0); gather<8>(b1, m1); gather<9>(b2, m2); gather<10>(b3, m3);
-        gather<11>(b4, m4); gather<12>(b5, m5); gather<13>(b6, m6);
-        update<7, ODD>(b0, m0); update<8, ODD>(b1, m1); update<9, ODD>(b2, m2); update<10, ODD>(b3, m3);
-        update<11, ODD>(b4, m4); update<12, ODD>(b5, m5); update<13, ODD>(b6, m6);
-        gather<14>(b0, m0); gather<15>(b1, m1); gather<16>(b2, m2); gather<17>(b3, m3);
-        gather<18>(b4, m4); gather<19>(b5, m5);
-        update<14, ODD>(b0, m0); update<15, ODD>(b1, m1); update<16, ODD>(b2, m2); update<17, ODD>(b3, m3);
-        update<18, ODD>(b4, m4); update<19, ODD>(b5, m5);
+        uint32_t b[7], m[7];
+        gather<0>(b[0], m[0]); gather<1>(b[1], m[1]); gather<2>(b[2], m[2]); gather<3>(b[3], m[3]);
+        gather<4>(b[4], m[4]); gather<5>(b[5], m[5]); gather<6>(b[6], m[6]);
+#define PDSAT_MT_STEP(J)                     \
+    update<J, ODD>(b[(J) % 7], m[(J) % 7]); \
+    if ((J) + 7 < 20) gather<((J) + 7 < 20 ? (J) + 7 : 0)>(b[(J) % 7], m[(J) % 7]);
+        PDSAT_MT_STEP(0) PDSAT_MT_STEP(1) PDSAT_MT_STEP(2) PDSAT_MT_STEP(3) PDSAT_MT_STEP(4)
+        PDSAT_MT_STEP(5) PDSAT_MT_STEP(6) PDSAT_MT_STEP(7) PDSAT_MT_STEP(8) PDSAT_MT_STEP(9)
+        PDSAT_MT_STEP(10) PDSAT_MT_STEP(11) PDSAT_MT_STEP(12) PDSAT_MT_STEP(13) PDSAT_MT_STEP(14)
+        PDSAT_MT_STEP(15) PDSAT_MT_STEP(16) PDSAT_MT_STEP(17) PDSAT_MT_STEP(18) PDSAT_MT_STEP(19)
+#undef PDSAT_MT_STEP
     }
 };
 
@@ -1591,15 +1596,26 @@ __device__ __forceinline__ void bcp_body(const DbDev& db, const BatchDev& b, int
             __syncthreads();  // all of my sums are on their way before the scratch is cleared
             // gather: wait for this step's packets of every rank in my own buffer, add, publish
             const volatile unsigned long long* mine = b.peer.shared[me] + (size_t)b.peer.parity * MAX_PEERS * 2 * nw;
+            unsigned long long t_start;
+            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_start));
             for (int i = threadIdx.x; i < nw; i += blockDim.x) {
                 unsigned long long sum = 0;
                 for (int src = 0; src < nr; src++) {
                     const volatile unsigned long long* q = mine + (size_t)src * 2 * nw + 2 * i;
-                    unsigned long long lo, hi;
-                    do lo = q[0];
-                    while ((uint32_t)(lo >> 32) != tag);
-                    do hi = q[1];
-                    while ((uint32_t)(hi >> 32) != tag);
+                    unsigned long long lo = q[0], hi = q[1];
+                    uint32_t spins = 0;
+                    while ((uint32_t)(lo >> 32) != tag || (uint32_t)(hi >> 32) != tag) {
+                        if ((++spins & 0xfffu) == 0) {
+                            unsigned long long t_now;
+                            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_now));
+                            if (t_now - t_start > PEER_TIMEOUT_NS) {
+                                *b.peer.timed_out = 1u;
+                                break;
+                            }
+                        }
+                        lo = q[0];
+                        hi = q[1];
+                    }
                     sum += (hi << 32) | (uint32_t)lo;
                 }
                 b.cost[i] = sum;

@@ -472,8 +472,8 @@ static void mt_plan(HostPoint& hp) {
 
 // Segments (= generator warps) a batch cuts its mt19937 streams into.  More segments keep more
 // schedulers busy in mt19937_bits_kernel but every segment costs one jump-ahead: a batch that is
-// alone on its device gets ~4 per SM; when several batches with mt19937 points are alive on the
-// device (a pipeline of handles, several search workers) their generator kernels overlap on
+// alone on its device gets ~4 per SM; when four or more batches with mt19937 points are alive on
+// the device (a pipeline of handles, several search workers) their generator kernels overlap on
 // the SMs and half as many segments per batch is the better trade (measured: profiles/README.md).
 static std::atomic<int> g_mt_batches[64];
 static int mt_target_segments(int device) {
@@ -481,7 +481,7 @@ static int mt_target_segments(int device) {
     int t = e ? atoi(e) : 0;
     if (t > 0) return t;
     const int alive = device >= 0 && device < 64 ? g_mt_batches[device].load() : 1;
-    return alive >= 2 ? 296 : 592;
+    return alive >= 4 ? 296 : 592;
 }
 
 int pdsat_batch_create(pdsat_db* db, int32_t n_points, const pdsat_point* points, uint32_t out_flags,
@@ -691,8 +691,8 @@ int pdsat_batch_create(pdsat_db* db, int32_t n_points, const pdsat_point* points
     CUB(cudaMemset(b->d_cost, 0, sizeof(unsigned long long) * PDSAT_COST_WORDS * n_points));
     CUB(cudaMalloc(&b->d_cost2, sizeof(unsigned long long) * PDSAT_COST_WORDS * n_points));
     CUB(cudaMemset(b->d_cost2, 0, sizeof(unsigned long long) * PDSAT_COST_WORDS * n_points));
-    CUB(cudaMalloc(&b->d_cta_done, sizeof(unsigned int)));
-    CUB(cudaMemset(b->d_cta_done, 0, sizeof(unsigned int)));
+    CUB(cudaMalloc(&b->d_cta_done, 2 * sizeof(unsigned int)));  // [0] ticket, [1] peer time-out flag
+    CUB(cudaMemset(b->d_cta_done, 0, 2 * sizeof(unsigned int)));
     CUB(cudaMalloc(&b->d_model_count, sizeof(unsigned long long)));
     if (b->max_models > 0) {
         CUB(cudaMalloc(&b->d_model_bits, sizeof(uint32_t) * (size_t)b->max_models * b->model_words));
@@ -1080,6 +1080,7 @@ int pdsat_batch_propagate(pdsat_batch* b) {
         bd.peer.parity = parity;
         bd.peer.n_words = n_cost_words;
         bd.peer.tag = (uint32_t)(b->peer_step + 1);
+        bd.peer.timed_out = b->d_cta_done + 1;
     }
     if (L.plane_bits == 64) bcp_kernel<<<grid, L.wpc * 32, L.smem_bytes, st>>>(dev, bd, L.warp_bytes);
     else bcp_kernel_h<<<grid, L.wpc * 32, L.smem_bytes, st>>>(dev, bd, L.warp_bytes);
@@ -1149,7 +1150,11 @@ int pdsat_batch_costs(pdsat_batch* b, pdsat_cost* out) {
     static_assert(sizeof(pdsat_cost) == 8 * PDSAT_COST_WORDS, "pdsat_cost layout");
     unsigned long long* cost = b->cost_ptr();
     CU(cudaMemcpyAsync(out, cost, sizeof(pdsat_cost) * b->pts.size(), cudaMemcpyDeviceToHost, b->db->stream));
+    unsigned int timed_out = 0;
+    if (b->peer_ranks > 0)
+        CU(cudaMemcpyAsync(&timed_out, b->d_cta_done + 1, sizeof(unsigned int), cudaMemcpyDeviceToHost, b->db->stream));
     CU(cudaStreamSynchronize(b->db->stream));
+    if (timed_out) return fail(PDSAT_ERR_CUDA, "peer exchange timed out: a rank did not launch its step");
     return PDSAT_OK;
 }
 
