@@ -1130,9 +1130,8 @@ __device__ __forceinline__ void bcp_body(const DbDev& db, const BatchDev& b, int
     if (lane == 0)
         for (int s = 0; s < stages; s++) prefetch_one();
 
-    // the index blob is waited for by the first group that propagates (streaming points never
-    // look at it) or, at the latest, before the CTA leaves
-    bool blob_ready = !db.blob_in_smem;
+    // the index blob is waited for by the groups that propagate (streaming points never look at
+    // it) and, at the latest, before the CTA leaves
     // CTA accumulator of the final flush: the first warp to finish names the point
     __shared__ unsigned long long s_acc[8];
     __shared__ int s_point;
@@ -1146,7 +1145,7 @@ __device__ __forceinline__ void bcp_body(const DbDev& db, const BatchDev& b, int
     // current point, cached in registers (a warp usually stays inside one point for many groups)
     int p = -1, p_prev = -1;
     uint64_t P_start = 0, P_end = 0, P_n_samples = 0, P_run_start = 0, P_run_end = 0;
-    uint32_t k = 0, P_var_off = 0, P_n_assumed = 0, P_cand_off = 0, P_cand_cnt = 0, P_code0 = 0, P_flags = 0, P_tile = 1;
+    uint32_t k = 0, P_var_off = 0, P_n_assumed = 0, P_cand_off = 0, P_cand_cnt = 0, P_code0 = 0, P_flags = 0;
     int stage = 0;
     uint32_t phase = 0;
     for (uint64_t run = r_first; run < b.n_runs; run += stride) {
@@ -1157,12 +1156,12 @@ __device__ __forceinline__ void bcp_body(const DbDev& db, const BatchDev& b, int
             if (p == 0) {  // from the kernel parameters
                 P_start = b.p0.group_start, P_run_start = b.p0.run_start, P_n_samples = b.p0.n_samples;
                 k = b.p0.k, P_var_off = b.p0.var_off, P_n_assumed = b.p0.n_assumed_live;
-                P_cand_off = b.p0.cand_off, P_cand_cnt = b.p0.cand_cnt, P_flags = b.p0.flags, P_tile = b.p0.tile;
+                P_cand_off = b.p0.cand_off, P_cand_cnt = b.p0.cand_cnt, P_flags = b.p0.flags;
             } else {
                 const PointDev* pt = &b.points[p];
                 P_start = pt->group_start, P_run_start = pt->run_start, P_n_samples = pt->n_samples;
                 k = pt->k, P_var_off = pt->var_off, P_n_assumed = pt->n_assumed_live;
-                P_cand_off = pt->cand_off, P_cand_cnt = pt->cand_cnt, P_flags = pt->flags, P_tile = pt->tile;
+                P_cand_off = pt->cand_off, P_cand_cnt = pt->cand_cnt, P_flags = pt->flags;
             }
             P_code0 = lane < (int)k ? b.setcode[P_var_off + lane] : 0u;
             flush_acc(accs, p_prev, b.acc, lane);
@@ -1180,7 +1179,7 @@ __device__ __forceinline__ void bcp_body(const DbDev& db, const BatchDev& b, int
             const uint64_t g_last = P_end - 1;  // the only group of the point that can be ragged
             const uint32_t n_tail = (uint32_t)(P_n_samples - (g_last - P_start) * 64);
             const bool want_out = b.conflict_bits != nullptr || b.trail != nullptr;
-            const uint32_t T = P_tile;
+            const uint32_t T = p == 0 ? b.p0.tile : b.points[p].tile;
             uint32_t cnt = 0;
             while (true) {
                 mbar_wait_s(bar_s + (uint32_t)stage * 8u, phase);  // the tile has landed (and is not needed)
@@ -1225,10 +1224,7 @@ __device__ __forceinline__ void bcp_body(const DbDev& db, const BatchDev& b, int
         }
 
         // a point in which BCP can start has runs of one group
-        if (!blob_ready) {
-            mbar_wait(blob_bar, 0);
-            blob_ready = true;
-        }
+        if (db.blob_in_smem) mbar_wait(blob_bar, 0);  // returns at once after the first time
         const uint64_t gi = run - P_run_start;
         const uint64_t g = P_start + gi;
         const uint64_t s0 = gi * 64;
@@ -1536,7 +1532,7 @@ __device__ __forceinline__ void bcp_body(const DbDev& db, const BatchDev& b, int
         }
     }
     TL(3);
-    if (!blob_ready) mbar_wait(blob_bar, 0);  // no bulk copy may be in flight when the CTA exits
+    if (db.blob_in_smem) mbar_wait(blob_bar, 0);  // no bulk copy may be in flight when the CTA exits
     TL(4);
 
     // ---- final flush: the warps that end in the same point as the first warp to finish (usually
