@@ -2,11 +2,12 @@
 
 ncu's CSV source page is SASS-level; nvdisasm --print-line-info on the cubin of the shipped .so
 gives the line of every SASS offset.  The two are joined on the offset inside the kernel.
-usage: python tools/ncu_lines.py <rep> <kernel-substring> [top N]"""
+usage: python tools/ncu_lines.py <rep> <mangled-name-substring> [top N] [ncu kernel regex]"""
 import csv, io, os, re, subprocess, sys, tempfile, collections
 
 rep, kern = sys.argv[1], sys.argv[2]
 top = int(sys.argv[3]) if len(sys.argv) > 3 else 40
+ncu_kern = sys.argv[4] if len(sys.argv) > 4 else kern
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 so = os.path.join(ROOT, "pdsat_b200", "libpdsat_b200.so")
 tmp = tempfile.mkdtemp()
@@ -27,7 +28,7 @@ for l in dis.splitlines():
     m = re.match(r"\s+/\*([0-9a-f]{4,})\*/\s+(.*);", l)
     if m:
         line_of[int(m.group(1), 16)] = (cur, m.group(2).strip())
-raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "-k", "regex:" + kern], capture_output=True, text=True).stdout
+raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "-k", "regex:" + ncu_kern], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 hi = [i for i, r in enumerate(rows) if r and r[0] == "Address"][0]
 hdr = rows[hi]
