@@ -1634,8 +1634,10 @@ __global__ void __launch_bounds__(512, 1) bcp_kernel(DbDev db, BatchDev b, int w
     bcp_body<uint64_t>(db, b, warp_bytes, smem, &blob_bar);
 }
 
-// 32-bit planes: half the shared memory per warp, up to 24 warps per CTA (<= 85 registers per thread)
-__global__ void __launch_bounds__(768, 1) bcp_kernel_h(DbDev db, BatchDev b, int warp_bytes) {
+// 32-bit planes: half the shared memory per warp.  Chosen only where fewer than 4 warps of full
+// planes fit (launch_shape), i.e. for large instances with a handful of warps per CTA: 8 warps at
+// most, which leaves the compiler 255 registers (at 768 threads this kernel spilled)
+__global__ void __launch_bounds__(256, 1) bcp_kernel_h(DbDev db, BatchDev b, int warp_bytes) {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ __align__(8) uint64_t blob_bar;
     bcp_body<uint32_t>(db, b, warp_bytes, smem, &blob_bar);

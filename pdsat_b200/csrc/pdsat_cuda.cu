@@ -242,7 +242,7 @@ static LaunchShape launch_shape_bits(const pdsat_db* db, uint32_t stage_bytes, i
     // the index blob is staged in shared memory only where that costs no resident warp (measured:
     // ODLS 4 warps + staged blob 4.36e8 samples/s, 6 warps + blob through L1/L2 4.80e8; Bivium has
     // room for both)
-    const int cap = plane_bits == 64 ? 16 : 24;  // __launch_bounds__(512) / (768)
+    const int cap = plane_bits == 64 ? 16 : 8;  // __launch_bounds__(512) / (256)
     const int wpc_without = std::min(cap, MAX_SMEM / L.warp_bytes);
     const int wpc_with = blob + L.warp_bytes <= MAX_SMEM ? std::min(cap, (MAX_SMEM - blob) / L.warp_bytes) : 0;
     L.blob_in_smem = (blob <= 64 * 1024 && wpc_with >= 1 && wpc_with == wpc_without) ? 1 : 0;
