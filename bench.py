@@ -217,8 +217,11 @@ def run_reference(args):
         return
     n_per_core = args.cpu_samples
     cores = os.cpu_count() or 1
-    for _ in range(min(args.warmup, 1)):
-        cpu_arm(max(20, n_per_core // 10))
+    # one calibration pass (also the warm-up); the per-step sample is bounded so that the K steps
+    # together stay near 90 s of wall clock whatever K the caller asks for
+    cal = cpu_arm(max(20, n_per_core // 10))
+    per_core_rate = cal["value"] / cores
+    n_per_core = int(max(20, min(n_per_core, 90.0 * per_core_rate / max(1, args.steps))))
     t_all = 0.0
     last = None
     for _ in range(args.steps):
