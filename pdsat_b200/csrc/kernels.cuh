@@ -225,34 +225,35 @@ __global__ void __launch_bounds__(FILL_STREAM_WARPS * 32) fill_stream_kernel(Bat
     const uint64_t g = (uint64_t)blockIdx.x * FILL_STREAM_WARPS + (threadIdx.x >> 5);
     if (g >= b.n_groups) return;
     const int lane = threadIdx.x & 31;
-    const PointDev& pt = b.points[find_point(b.points, b.n_points, g)];
+    const PointDev& pt = b.points[b.n_points == 1 ? 0 : find_point(b.points, b.n_points, g)];
     if (pt.mode != 0 && pt.mode != 3) return;  // PDSAT_MODE_RANDOM_MT19937 / PDSAT_MODE_EXPLICIT
     const uint64_t gi = g - pt.group_start;
     const uint64_t s0 = gi * 64;
     const uint64_t left = pt.n_samples - s0;
     const uint32_t ns = left < 64 ? (uint32_t)left : 64u;
-    const uint32_t k = pt.k;
-    const uint32_t* st = b.stream + pt.stream_off;
-    uint64_t* dst = b.words + pt.word_off + gi * pt.kp;
-    const uint64_t d0 = pt.stream_skip + s0 * k;
-    for (uint32_t c = 0; c < pt.kp; c += 32) {
+    const uint32_t k = pt.k, kp = pt.kp;
+    const uint64_t d0 = pt.stream_skip + s0 * k;                   // first bit of the group in the stream
+    const uint32_t* st = b.stream + pt.stream_off + (d0 >> 5);      // its word; inside the group 32-bit offsets do
+    const uint32_t sh0 = (uint32_t)(d0 & 31);
+    uint64_t* dst = b.words + pt.word_off + gi * kp;
+    for (uint32_t c = 0; c < kp; c += 32) {
         const uint32_t nb = c < k ? (k - c < 32 ? k - c : 32u) : 0u;  // columns of this block
+        const uint32_t keep = nb < 32 ? (1u << nb) - 1u : 0xffffffffu;
         uint32_t half[2];
 #pragma unroll
         for (int h = 0; h < 2; h++) {
             const uint32_t s = lane + 32 * h;
             uint32_t row = 0;
             if (s < ns && nb) {
-                const uint64_t d = d0 + (uint64_t)s * k + c;
-                const uint32_t sh = (uint32_t)(d & 31);
+                const uint32_t d = sh0 + s * k + c;  // < 32 + 64 * k + k: fits 32 bits for every k the ABI allows
+                const uint32_t sh = d & 31;
                 const uint32_t lo = __ldg(st + (d >> 5));
                 const uint32_t hi = sh + nb > 32 ? __ldg(st + (d >> 5) + 1) : 0u;
-                row = __funnelshift_r(lo, hi, sh);
-                if (nb < 32) row &= (1u << nb) - 1u;
+                row = __funnelshift_r(lo, hi, sh) & keep;
             }
             half[h] = warp_transpose32(row, lane);
         }
-        if (c + lane < pt.kp) dst[c + lane] = (uint64_t)half[0] | ((uint64_t)half[1] << 32);
+        if (c + lane < kp) dst[c + lane] = (uint64_t)half[0] | ((uint64_t)half[1] << 32);
     }
 }
 
