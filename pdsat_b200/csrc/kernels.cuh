@@ -93,6 +93,19 @@ struct PeerDev {
     int32_t n_words;                        // accumulators = n_points * 8
     uint32_t tag;                           // step number + 1 (never 0)
     unsigned int* timed_out;                // set when a peer's packets did not arrive within PEER_TIMEOUT_NS
+    // Deferred exchange.  Launch t only ADDS into its own scratch (acc[t & 1]); nothing is sent
+    // and nobody waits at the end of a launch.  CTA 0 of launch t+1 - while the other CTAs already
+    // work - first gathers the packets of step t-1 (sent by the peers one launch ago), then pushes
+    // the sums of step t and clears their scratch.  When the host asks for the costs,
+    // peer_finish_kernel does the same two things and gathers step t as well (the ranks ask at the
+    // same step).  Order matters: gather before push.  A rank's push of step t overwrites the
+    // parity that carried step t-2; it comes after the rank has seen every peer's packets of t-1,
+    // which every peer sends after ITS gather of t-2 - so two parities suffice.
+    int32_t gather_prev;                    // 1: gather (g_parity, g_tag) first
+    int32_t g_parity;
+    uint32_t g_tag;
+    int32_t push_prev;                      // 1: then push acc_prev as (parity, tag) and clear it
+    unsigned long long* acc_prev;
 };
 // a rank that never launches its step (crashed, or the caller broke the "same calls on every
 // rank" rule) must not leave the others spinning for ever: the wait gives up and the host
@@ -116,6 +129,7 @@ struct BatchDev {
     unsigned long long* zero_next;  // direct path (no peers, library-owned buffers): acc IS the output
                                     // of this launch, CTA 0 clears zero_next (= the next launch's) and
                                     // nobody publishes; nullptr: ticket path
+    int32_t no_ticket;          // direct path or peers: the launch ends with the CTAs' adds (no last-CTA pass)
     PointDev p0;                // point 0 again, in the kernel parameters: the first tile of a one-point
                                 // batch is requested without a global load in front of it
     uint64_t* conflict_bits;    // per global group (optional)
@@ -1012,6 +1026,72 @@ __device__ __forceinline__ void count_planes(const PT* S, const uint32_t* set, i
 // With 32-bit planes (1) - (5) run twice per group, once per half.
 // A point without candidates and without level-0-fixed set variables cannot start BCP at all:
 // its groups skip (1), (2), (3) and (5) - the words still stream through the ring.
+// ---- cost exchange over NVLink peer memory (PeerDev).  Block-wide helpers.
+// gather: wait for the packets of every rank for (parity, tag) in this rank's own buffer, add
+// them and (publish) write the totals into b.cost
+__device__ __forceinline__ void peer_gather(const BatchDev& b, int parity, uint32_t tag, bool publish) {
+    const int nw = b.n_points * 8, nr = b.peer.n_ranks;
+    const volatile unsigned long long* mine = b.peer.shared[b.peer.me] + (size_t)parity * MAX_PEERS * 2 * nw;
+    unsigned long long t_start;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_start));
+    for (int i = threadIdx.x; i < nw; i += blockDim.x) {
+        unsigned long long sum = 0;
+        for (int src = 0; src < nr; src++) {
+            const volatile unsigned long long* q = mine + (size_t)src * 2 * nw + 2 * i;
+            unsigned long long lo = q[0], hi = q[1];
+            uint32_t spins = 0;
+            while ((uint32_t)(lo >> 32) != tag || (uint32_t)(hi >> 32) != tag) {
+                if ((++spins & 0xfffu) == 0) {
+                    unsigned long long t_now;
+                    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_now));
+                    if (t_now - t_start > PEER_TIMEOUT_NS) {
+                        *b.peer.timed_out = 1u;
+                        break;
+                    }
+                }
+                lo = q[0];
+                hi = q[1];
+            }
+            sum += (hi << 32) | (uint32_t)lo;
+        }
+        if (publish) b.cost[i] = sum;
+    }
+}
+
+// push: this rank's sums of the launch before (acc_prev) as tagged packets into its slot of every
+// rank's buffer, then clear them; every rank starts with a different target so that the ranks
+// do not all hit the same peer at once
+__device__ __forceinline__ void peer_push(const BatchDev& b) {
+    const int nw = b.n_points * 8, nr = b.peer.n_ranks, me = b.peer.me;
+    const uint32_t tag = b.peer.tag;
+    const size_t slot = ((size_t)b.peer.parity * MAX_PEERS + me) * 2 * nw;
+    for (int j = threadIdx.x; j < 2 * nw * nr; j += blockDim.x) {
+        const int e = j % (2 * nw);
+        const int r = (j / (2 * nw) + me) % nr;
+        const unsigned long long v = __ldcg(&b.peer.acc_prev[e >> 1]);
+        const unsigned long long pkt = ((unsigned long long)tag << 32) | (uint32_t)((e & 1) ? (v >> 32) : v);
+        *((volatile unsigned long long*)&b.peer.shared[r][slot + e]) = pkt;
+    }
+    __syncthreads();  // every packet is on its way before the scratch is cleared
+    for (int i = threadIdx.x; i < nw; i += blockDim.x) b.peer.acc_prev[i] = 0;
+}
+
+// what CTA 0 of a launch does first (see PeerDev)
+__device__ __forceinline__ void peer_catch_up(const BatchDev& b) {
+    if (b.peer.gather_prev) {
+        peer_gather(b, b.peer.g_parity, b.peer.g_tag, true);
+        __syncthreads();
+    }
+    if (b.peer.push_prev) peer_push(b);
+}
+
+// the host wants the totals of the last launch: catch up, then gather that step as well
+__global__ void __launch_bounds__(512) peer_finish_kernel(BatchDev b) {
+    peer_catch_up(b);
+    __syncthreads();
+    peer_gather(b, b.peer.parity, b.peer.tag, true);
+}
+
 template <typename PT>
 __device__ __forceinline__ void bcp_body(const DbDev& db, const BatchDev& b, int warp_bytes, unsigned char* smem,
                                          uint64_t* blob_bar) {
@@ -1141,6 +1221,7 @@ __device__ __forceinline__ void bcp_body(const DbDev& db, const BatchDev& b, int
     if (b.zero_next != nullptr && blockIdx.x == 0)  // direct path: clear the accumulators of the next launch
         for (int i = threadIdx.x; i < b.n_points * 8; i += blockDim.x) b.zero_next[i] = 0;
     __syncthreads();  // also: the blob barrier init is visible to everybody
+    if (b.peer.n_ranks > 0 && blockIdx.x == 0) peer_catch_up(b);  // while the other CTAs already work
     TL(1);
 
     // current point, cached in registers (a warp usually stays inside one point for many groups)
@@ -1561,12 +1642,12 @@ __device__ __forceinline__ void bcp_body(const DbDev& db, const BatchDev& b, int
         __syncthreads();
         TL(5);
         if (warp != 0) {
-            if (b.zero_next != nullptr) return;  // direct path: nothing to publish
+            if (b.no_ticket) return;  // direct path / peers: nothing to publish here
         } else {
             if (lane < 8 && s_point >= 0 && s_acc[lane]) atomicAdd(&b.acc[(size_t)s_point * 8 + lane], s_acc[lane]);
-            if (b.zero_next != nullptr) return;
-            // ---- ticket path: the last CTA publishes the accumulators, alone or after the exchange
-            // with the peers
+            if (b.no_ticket) return;
+            // ---- ticket path (caller-owned cost buffer, no peers): the last CTA publishes the
+            // scratch accumulators and clears them
             __threadfence();
             __syncwarp();
             if (lane == 0) s_ticket = atomicAdd(b.cta_done, 1u);
@@ -1576,49 +1657,7 @@ __device__ __forceinline__ void bcp_body(const DbDev& db, const BatchDev& b, int
         if (s_ticket != gridDim.x - 1) return;
         __threadfence();
         const int nw = b.n_points * 8;
-        if (b.peer.n_ranks > 0) {
-            // exchange the rank's sums with every peer (see PeerDev)
-            const int nr = b.peer.n_ranks, me = b.peer.me;
-            const uint32_t tag = b.peer.tag;
-            const size_t slot = ((size_t)b.peer.parity * MAX_PEERS + me) * 2 * nw;  // my slot in a receive buffer
-            // push: packet e of my slot on rank r; every rank starts with a different target so
-            // that the ranks do not all hit the same peer at the same moment
-            for (int j = threadIdx.x; j < 2 * nw * nr; j += blockDim.x) {
-                const int e = j % (2 * nw);
-                const int r = (j / (2 * nw) + me) % nr;
-                const unsigned long long v = __ldcg(&b.acc[e >> 1]);
-                const unsigned long long pkt = ((unsigned long long)tag << 32) | (uint32_t)((e & 1) ? (v >> 32) : v);
-                *((volatile unsigned long long*)&b.peer.shared[r][slot + e]) = pkt;
-            }
-            __syncthreads();  // all of my sums are on their way before the scratch is cleared
-            // gather: wait for this step's packets of every rank in my own buffer, add, publish
-            const volatile unsigned long long* mine = b.peer.shared[me] + (size_t)b.peer.parity * MAX_PEERS * 2 * nw;
-            unsigned long long t_start;
-            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_start));
-            for (int i = threadIdx.x; i < nw; i += blockDim.x) {
-                unsigned long long sum = 0;
-                for (int src = 0; src < nr; src++) {
-                    const volatile unsigned long long* q = mine + (size_t)src * 2 * nw + 2 * i;
-                    unsigned long long lo = q[0], hi = q[1];
-                    uint32_t spins = 0;
-                    while ((uint32_t)(lo >> 32) != tag || (uint32_t)(hi >> 32) != tag) {
-                        if ((++spins & 0xfffu) == 0) {
-                            unsigned long long t_now;
-                            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_now));
-                            if (t_now - t_start > PEER_TIMEOUT_NS) {
-                                *b.peer.timed_out = 1u;
-                                break;
-                            }
-                        }
-                        lo = q[0];
-                        hi = q[1];
-                    }
-                    sum += (hi << 32) | (uint32_t)lo;
-                }
-                b.cost[i] = sum;
-                b.acc[i] = 0;
-            }
-        } else {
+        {
             for (int i = threadIdx.x; i < nw; i += blockDim.x) {
                 b.cost[i] = __ldcg(&b.acc[i]);
                 b.acc[i] = 0;

@@ -121,6 +121,7 @@ struct pdsat_batch {
     bool timing = true, fill_timed = false, propagate_timed = false;  // pdsat_batch_set_timing
     int cost_cur = 0;          // buffer the last direct launch wrote
     bool last_direct = false;  // the last launch took the direct path
+    int last_path = 1;         // 0 direct, 1 ticket, 2 peers (buffers are zeroed when it changes)
     bool no_direct = false;    // the caller holds a device pointer to the costs: keep it stable
     unsigned long long* cost_ptr() const {
         if (last_direct) return cost_cur ? d_cost2 : d_cost;
@@ -166,6 +167,11 @@ struct pdsat_batch {
     size_t mt_seq_cap = 0;
     int peer_ranks = 0, peer_me = 0;
     uint64_t peer_step = 0;
+    // deferred exchange (PeerDev): after launch t the sums of step t sit in d_acc / d_acc2 unsent
+    // (peer_unsent) and, if step t-1 was not finished by the host, its packets are still to be
+    // gathered (peer_ungathered); the next launch's CTA 0 or peer_finalize catches up
+    bool peer_unsent = false, peer_ungathered = false;
+    unsigned long long* d_acc2 = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev_h2d = nullptr;  // the last fill's copies out of the pinned staging buffers
     bool h2d_pending = false;
@@ -688,11 +694,13 @@ int pdsat_batch_create(pdsat_db* db, int32_t n_points, const pdsat_point* points
     CUB(cudaMalloc(&b->d_cost, sizeof(unsigned long long) * PDSAT_COST_WORDS * n_points));
     CUB(cudaMalloc(&b->d_acc, sizeof(unsigned long long) * PDSAT_COST_WORDS * n_points));
     CUB(cudaMemset(b->d_acc, 0, sizeof(unsigned long long) * PDSAT_COST_WORDS * n_points));
+    CUB(cudaMalloc(&b->d_acc2, sizeof(unsigned long long) * PDSAT_COST_WORDS * n_points));
+    CUB(cudaMemset(b->d_acc2, 0, sizeof(unsigned long long) * PDSAT_COST_WORDS * n_points));
     CUB(cudaMemset(b->d_cost, 0, sizeof(unsigned long long) * PDSAT_COST_WORDS * n_points));
     CUB(cudaMalloc(&b->d_cost2, sizeof(unsigned long long) * PDSAT_COST_WORDS * n_points));
     CUB(cudaMemset(b->d_cost2, 0, sizeof(unsigned long long) * PDSAT_COST_WORDS * n_points));
-    CUB(cudaMalloc(&b->d_cta_done, 2 * sizeof(unsigned int)));  // [0] ticket, [1] peer time-out flag
-    CUB(cudaMemset(b->d_cta_done, 0, 2 * sizeof(unsigned int)));
+    CUB(cudaMalloc(&b->d_cta_done, 4 * sizeof(unsigned int)));  // [0] ticket, [1] peer time-out flag, [2] gather done
+    CUB(cudaMemset(b->d_cta_done, 0, 4 * sizeof(unsigned int)));
     CUB(cudaMalloc(&b->d_model_count, sizeof(unsigned long long)));
     if (b->max_models > 0) {
         CUB(cudaMalloc(&b->d_model_bits, sizeof(uint32_t) * (size_t)b->max_models * b->model_words));
@@ -1013,6 +1021,8 @@ int pdsat_batch_fill(pdsat_batch* b) {
     return PDSAT_OK;
 }
 
+static void peer_fill(pdsat_batch* b, BatchDev& bd);
+
 int pdsat_batch_propagate(pdsat_batch* b) {
     if (!b) return fail(PDSAT_ERR_ARG, "pdsat_batch_propagate: null batch");
     if (!b->filled) return fail(PDSAT_ERR_ARG, "pdsat_batch_propagate: batch not filled");
@@ -1022,10 +1032,13 @@ int pdsat_batch_propagate(pdsat_batch* b) {
     cudaStream_t st = db->stream;
     const bool direct = b->peer_ranks == 0 && !b->d_cost_ext && !b->no_direct;
     const size_t cost_bytes = sizeof(unsigned long long) * PDSAT_COST_WORDS * b->pts.size();
-    if (direct != b->last_direct) {  // path change (rare): both conventions start from zeroed buffers
+    const int path = direct ? 0 : (b->peer_ranks > 0 ? 2 : 1);  // direct / ticket / peers
+    if (path != b->last_path) {  // path change (rare): every convention starts from zeroed buffers
         CU(cudaMemsetAsync(b->d_cost, 0, cost_bytes, st));
         CU(cudaMemsetAsync(b->d_cost2, 0, cost_bytes, st));
         CU(cudaMemsetAsync(b->d_acc, 0, cost_bytes, st));
+        CU(cudaMemsetAsync(b->d_acc2, 0, cost_bytes, st));
+        b->last_path = path;
     }
     if (direct) b->cost_cur ^= 1;
     b->last_direct = direct;
@@ -1043,8 +1056,10 @@ int pdsat_batch_propagate(pdsat_batch* b) {
     bd.words = b->d_words;
     bd.stream = b->d_stream;
     bd.cost = cost;
-    bd.acc = direct ? cost : b->d_acc;
+    const int peer_par = (int)(b->peer_step & 1);
+    bd.acc = direct ? cost : (b->peer_ranks > 0 && peer_par ? b->d_acc2 : b->d_acc);
     bd.zero_next = direct ? (b->cost_cur ? b->d_cost : b->d_cost2) : nullptr;
+    bd.no_ticket = (direct || b->peer_ranks > 0) ? 1 : 0;
     bd.cta_done = b->d_cta_done;
     bd.p0 = b->h_points[0];
     bd.conflict_bits = b->d_conflict;
@@ -1072,20 +1087,15 @@ int pdsat_batch_propagate(pdsat_batch* b) {
     int grid = (int)(ctas_needed < (uint64_t)db->grid ? ctas_needed : (uint64_t)db->grid);
     if (grid < 1) grid = 1;
     const int n_cost_words = PDSAT_COST_WORDS * (int)b->pts.size();
-    const int parity = (int)(b->peer_step & 1);
-    if (b->peer_ranks > 0) {
-        for (int r = 0; r < b->peer_ranks; r++) bd.peer.shared[r] = b->peer_ptr[r];
-        bd.peer.n_ranks = b->peer_ranks;
-        bd.peer.me = b->peer_me;
-        bd.peer.parity = parity;
-        bd.peer.n_words = n_cost_words;
-        bd.peer.tag = (uint32_t)(b->peer_step + 1);
-        bd.peer.timed_out = b->d_cta_done + 1;
-    }
+    if (b->peer_ranks > 0) peer_fill(b, bd);  // what CTA 0 catches up on first (PeerDev)
     if (L.plane_bits == 64) bcp_kernel<<<grid, L.wpc * 32, L.smem_bytes, st>>>(dev, bd, L.warp_bytes);
     else bcp_kernel_h<<<grid, L.wpc * 32, L.smem_bytes, st>>>(dev, bd, L.warp_bytes);
     b->n_kernels++;
-    if (b->peer_ranks > 0) b->peer_step++;  // the exchange happens inside the kernel (its last CTA)
+    if (b->peer_ranks > 0) {  // the sums of this step stay in the scratch until the next launch / peer_finalize
+        b->peer_ungathered = b->peer_unsent;  // the launch pushes the step before (if it was still unsent)
+        b->peer_unsent = true;
+        b->peer_step++;
+    }
     CU(cudaGetLastError());
     if (b->timing) CU(cudaEventRecord(b->ev[3], st));
     b->propagate_timed = b->timing;
@@ -1093,8 +1103,45 @@ int pdsat_batch_propagate(pdsat_batch* b) {
     return PDSAT_OK;
 }
 
+// peers: the PeerDev fields of a launch (or of peer_finish_kernel) that follows `peer_step` steps.
+// Step numbers: the last launched step is t = peer_step - 1; tag = step + 1 (never 0).
+static void peer_fill(pdsat_batch* b, BatchDev& bd) {
+    for (int r = 0; r < b->peer_ranks; r++) bd.peer.shared[r] = b->peer_ptr[r];
+    bd.peer.n_ranks = b->peer_ranks;
+    bd.peer.me = b->peer_me;
+    bd.peer.n_words = PDSAT_COST_WORDS * (int)b->pts.size();
+    bd.peer.timed_out = b->d_cta_done + 1;
+    const uint64_t t = b->peer_step - 1;  // only read when something is pending (peer_step >= 1 then)
+    bd.peer.push_prev = b->peer_unsent ? 1 : 0;
+    bd.peer.parity = (int)(t & 1);
+    bd.peer.tag = (uint32_t)(t + 1);
+    bd.peer.acc_prev = (t & 1) ? b->d_acc2 : b->d_acc;
+    bd.peer.gather_prev = b->peer_ungathered ? 1 : 0;
+    bd.peer.g_parity = (int)((t - 1) & 1);
+    bd.peer.g_tag = (uint32_t)t;
+}
+
+// peers: the host wants the totals of the last launch now
+static int peer_finalize(pdsat_batch* b) {
+    if (b->peer_ranks == 0 || !b->peer_unsent) return PDSAT_OK;
+    CU(cudaSetDevice(b->db->device));
+    BatchDev bd{};
+    bd.n_points = (int32_t)b->pts.size();
+    bd.cost = b->cost_ptr();
+    peer_fill(b, bd);
+    peer_finish_kernel<<<1, 512, 0, b->db->stream>>>(bd);
+    b->n_kernels++;
+    CU(cudaGetLastError());
+    b->peer_unsent = b->peer_ungathered = false;
+    return PDSAT_OK;
+}
+
 int pdsat_batch_sync(pdsat_batch* b) {
     if (!b) return fail(PDSAT_ERR_ARG, "pdsat_batch_sync: null batch");
+    {
+        const int rc = peer_finalize(b);
+        if (rc) return rc;
+    }
     CU(cudaStreamSynchronize(b->db->stream));
     return PDSAT_OK;
 }
@@ -1140,6 +1187,10 @@ int pdsat_batch_cost_device_ptr(pdsat_batch* b, void** dptr) {
 
 int pdsat_batch_set_cost_buffer(pdsat_batch* b, void* dptr) {
     if (!b) return fail(PDSAT_ERR_ARG, "pdsat_batch_set_cost_buffer: null batch");
+    {  // sums still to be gathered go where the caller expected them when it launched
+        const int rc = peer_finalize(b);
+        if (rc) return rc;
+    }
     b->d_cost_ext = (unsigned long long*)dptr;
     return PDSAT_OK;
 }
@@ -1148,6 +1199,10 @@ int pdsat_batch_costs(pdsat_batch* b, pdsat_cost* out) {
     if (!b || !out) return fail(PDSAT_ERR_ARG, "pdsat_batch_costs: bad argument");
     if (!b->propagated) return fail(PDSAT_ERR_ARG, "pdsat_batch_costs: batch not propagated");
     static_assert(sizeof(pdsat_cost) == 8 * PDSAT_COST_WORDS, "pdsat_cost layout");
+    {
+        const int rc = peer_finalize(b);
+        if (rc) return rc;
+    }
     unsigned long long* cost = b->cost_ptr();
     CU(cudaMemcpyAsync(out, cost, sizeof(pdsat_cost) * b->pts.size(), cudaMemcpyDeviceToHost, b->db->stream));
     unsigned int timed_out = 0;
@@ -1216,6 +1271,10 @@ int pdsat_batch_models(pdsat_batch* b, int64_t* n_found, int32_t* point_of, uint
     if (b->max_models > 0) {
         CU(cudaMemcpy(&cnt, b->d_model_count, sizeof(cnt), cudaMemcpyDeviceToHost));
     } else {  // nothing is stored: the count is the sum of the points' n_full
+        {
+            const int rc = peer_finalize(b);
+            if (rc) return rc;
+        }
         std::vector<pdsat_cost> c(b->pts.size());
         unsigned long long* cost = b->cost_ptr();
         CU(cudaMemcpy(c.data(), cost, sizeof(pdsat_cost) * c.size(), cudaMemcpyDeviceToHost));
@@ -1282,11 +1341,15 @@ int pdsat_batch_peer_connect(pdsat_batch* b, int32_t n_ranks, int32_t my_rank, c
     b->peer_ranks = n_ranks;
     b->peer_me = my_rank;
     b->peer_step = 0;
+    b->peer_unsent = b->peer_ungathered = false;
+    CU(cudaMemset(b->d_cta_done, 0, 4 * sizeof(unsigned int)));
     return PDSAT_OK;
 }
 
 int pdsat_batch_peer_disconnect(pdsat_batch* b) {
     if (!b) return fail(PDSAT_ERR_ARG, "pdsat_batch_peer_disconnect: null batch");
+    if (b->db && b->db->device >= 0 && b->peer_ranks > 0) peer_finalize(b);  // nothing of this rank stays unsent
+    b->peer_unsent = b->peer_ungathered = false;
     if (b->db && b->db->device >= 0) {
         cudaSetDevice(b->db->device);
         if (b->db->stream) cudaStreamSynchronize(b->db->stream);
@@ -1317,6 +1380,7 @@ void pdsat_batch_destroy(pdsat_batch* b) {
     cudaFree(b->d_cost);
     cudaFree(b->d_cost2);
     cudaFree(b->d_acc);
+    cudaFree(b->d_acc2);
     cudaFree(b->d_conflict);
     cudaFree(b->d_full);
     cudaFree(b->d_trail);
