@@ -1035,10 +1035,23 @@ __device__ __forceinline__ void peer_gather(const BatchDev& b, int parity, uint3
     unsigned long long t_start;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_start));
     for (int i = threadIdx.x; i < nw; i += blockDim.x) {
+        // all sources' packets are requested before the first tag is looked at: in the steady
+        // state they arrived a launch ago and the gather costs one L2 round trip, not one per rank
+        unsigned long long lo_[MAX_PEERS], hi_[MAX_PEERS];
+#pragma unroll
+        for (int src = 0; src < MAX_PEERS; src++) {
+            if (src < nr) {
+                const volatile unsigned long long* q = mine + (size_t)src * 2 * nw + 2 * i;
+                lo_[src] = q[0];
+                hi_[src] = q[1];
+            }
+        }
         unsigned long long sum = 0;
-        for (int src = 0; src < nr; src++) {
+#pragma unroll
+        for (int src = 0; src < MAX_PEERS; src++) {
+            if (src >= nr) break;
             const volatile unsigned long long* q = mine + (size_t)src * 2 * nw + 2 * i;
-            unsigned long long lo = q[0], hi = q[1];
+            unsigned long long lo = lo_[src], hi = hi_[src];
             uint32_t spins = 0;
             while ((uint32_t)(lo >> 32) != tag || (uint32_t)(hi >> 32) != tag) {
                 if ((++spins & 0xfffu) == 0) {
