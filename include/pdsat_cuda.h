@@ -204,15 +204,20 @@ int pdsat_batch_cost_device_ptr(pdsat_batch* b, void** dptr);
 int pdsat_batch_set_cost_buffer(pdsat_batch* b, void* dptr);
 int pdsat_batch_costs(pdsat_batch* b, pdsat_cost* out /* n_points */);
 
-/* Multi-GPU, one process per GPU: cost all-reduce FUSED into the BCP kernel over NVLink peer
- * memory instead of a separate collective.  Every rank exports a 64-byte CUDA IPC handle of its
+/* Multi-GPU, one process per GPU: cost all-reduce through the BCP kernel over NVLink peer memory
+ * instead of a separate collective.  Every rank exports a 64-byte CUDA IPC handle of its
  * receive buffer, the ranks exchange the handles out of band (all_gather of 64 bytes), every
- * rank connects; from then on pdsat_batch_propagate is COLLECTIVE (all ranks must call it the
- * same number of times) and leaves the summed accumulators of ALL ranks in the cost buffer.
- * Inside the kernel: the last CTA stores the rank's sums as tagged 8-byte packets into every
- * peer's buffer and gathers the peers' packets from its own (no fence, no atomics, no second
- * kernel).  Replaces the ncclAllReduce of SURVEY.md 8(e); results are identical (integer sums).
- * Use it with one rank per GPU only: ranks that wait for each other must run concurrently. */
+ * rank connects; from then on the sequence pdsat_batch_propagate ... pdsat_batch_costs is
+ * COLLECTIVE (all ranks launch the same steps and ask for the costs at the same steps) and
+ * pdsat_batch_costs returns the summed accumulators of ALL ranks.
+ * The exchange is deferred: a launch only adds into the rank's scratch; CTA 0 of the next launch
+ * gathers the peers' tagged 8-byte packets of the step before and pushes this rank's sums into
+ * every peer's buffer while the other CTAs already work (no fence, no atomics, no waiting at the
+ * end of a launch); pdsat_batch_costs / pdsat_batch_sync finish the last step with a one-CTA
+ * kernel.  The totals are therefore valid after those two calls, not in stream order after
+ * pdsat_batch_propagate.  A wait for a rank that never launched its step gives up after 20 s
+ * (PDSAT_ERR_CUDA from pdsat_batch_costs).  Replaces the ncclAllReduce of SURVEY.md 8(e);
+ * results are identical (integer sums).  Use it with one rank per GPU only. */
 #define PDSAT_IPC_HANDLE_BYTES 64
 int pdsat_batch_peer_export(pdsat_batch* b, void* handle_out /* 64 bytes */);
 int pdsat_batch_peer_connect(pdsat_batch* b, int32_t n_ranks, int32_t my_rank,
