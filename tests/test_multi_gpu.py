@@ -63,6 +63,10 @@ def test_two_gpu_matches_one_gpu(cuda_lib):
         assert g == [r.cost.n, r.cost.n_conflict, r.cost.n_full, r.cost.sum_trail, r.cost.sumsq_trail]
 
 
+BURSTS = [(5, False), (6, False), (7, True), (8, False), (9, True), (10, True), (11, False), (12, False),
+          (13, False), (14, False), (15, True)]
+
+
 def _peer_worker(rank, world, port, n, q):
     sys.path.insert(0, ROOT)
     import torch
@@ -93,6 +97,15 @@ def _peer_worker(rank, world, port, n, q):
             b.reseed(p, 1 + p + 10 * step, pts[p].first_sample)
         c = b.run()
         out.append([[x.n, x.n_conflict, x.n_full, x.sum_trail, x.sumsq_trail] for x in c])
+    # the deferred exchange: launches whose costs are never asked for (their sums are pushed and
+    # gathered by the launches that follow), then a read; bursts of different lengths
+    for step, read in BURSTS:
+        for p in range(len(pts)):
+            b.reseed(p, 1 + p + 10 * step, pts[p].first_sample)
+        b.fill()
+        b.propagate()
+        if read:
+            out.append([[x.n, x.n_conflict, x.n_full, x.sum_trail, x.sumsq_trail] for x in b.costs()])
     q.put((rank, out))
     dist.barrier()
     b.close()
@@ -123,7 +136,9 @@ def test_fused_peer_reduce_matches_one_gpu(cuda_lib):
     db = api.ClauseDb(nv, offs, lits, device=0)
     db.set_fixed_assumptions(stream)
     sets = [list(range(148, 178)), [177 - i for i in range(86)]]
-    for step in range(5):
+    read_steps = list(range(5)) + [st for st, read in BURSTS if read]
+    assert len(got[0]) == len(read_steps)
+    for i, step in enumerate(read_steps):
         costs = db.eval_batch([api.Point(sv, n, api.MODE_MT19937, seed=1 + p + 10 * step) for p, sv in enumerate(sets)])
         exp = [[x.n, x.n_conflict, x.n_full, x.sum_trail, x.sumsq_trail] for x in costs]
-        assert got[0][step] == exp, step
+        assert got[0][i] == exp, step
