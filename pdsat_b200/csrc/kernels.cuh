@@ -1114,6 +1114,9 @@ __device__ __forceinline__ void bcp_body(const DbDev& db, const BatchDev& b, int
     const int warp = threadIdx.x >> 5;
     const int wpc = blockDim.x >> 5;
     TL(0);
+    // the next kernel in the stream (another propagate launched the same way) may start its own
+    // prologue as soon as SMs free up; it waits at its griddepcontrol.wait for this grid to finish
+    asm volatile("griddepcontrol.launch_dependents;");
 
     // ---- index blob (occurrence offsets, gate lists, gate records): one bulk copy per CTA into
     // shared memory when it fits, otherwise read from global / L2
@@ -1221,6 +1224,12 @@ __device__ __forceinline__ void bcp_body(const DbDev& db, const BatchDev& b, int
         pf_r += stride;
         pf_stage = pf_stage + 1 == (uint32_t)stages ? 0 : pf_stage + 1;
     };
+    // Programmatic dependent launch: the host launches this kernel with programmatic stream
+    // serialisation, so its CTAs may start while the kernel before it in the stream is draining.
+    // Everything above touches only this CTA's shared memory and data that is constant since the
+    // upload; from here on the kernel reads what the fill stage wrote and writes accumulators the
+    // launch before may still be adding to: wait for the prerequisite grid to complete and flush.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     if (lane == 0)
         for (int s = 0; s < stages; s++) prefetch_one();
 

@@ -1088,8 +1088,24 @@ int pdsat_batch_propagate(pdsat_batch* b) {
     if (grid < 1) grid = 1;
     const int n_cost_words = PDSAT_COST_WORDS * (int)b->pts.size();
     if (b->peer_ranks > 0) peer_fill(b, bd);  // what CTA 0 catches up on first (PeerDev)
-    if (L.plane_bits == 64) bcp_kernel<<<grid, L.wpc * 32, L.smem_bytes, st>>>(dev, bd, L.warp_bytes);
-    else bcp_kernel_h<<<grid, L.wpc * 32, L.smem_bytes, st>>>(dev, bd, L.warp_bytes);
+    {
+        // programmatic dependent launch (kernels.cuh: griddepcontrol): the prologue of this launch
+        // overlaps the tail of the kernel before it in the stream
+        static const bool use_pdl = getenv("PDSAT_NO_PDL") == nullptr;
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3((unsigned)grid);
+        cfg.blockDim = dim3((unsigned)(L.wpc * 32));
+        cfg.dynamicSmemBytes = (size_t)L.smem_bytes;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = use_pdl ? 1 : 0;
+        const int wb = L.warp_bytes;
+        if (L.plane_bits == 64) CU(cudaLaunchKernelEx(&cfg, bcp_kernel, dev, bd, wb));
+        else CU(cudaLaunchKernelEx(&cfg, bcp_kernel_h, dev, bd, wb));
+    }
     b->n_kernels++;
     if (b->peer_ranks > 0) {  // the sums of this step stay in the scratch until the next launch / peer_finalize
         b->peer_ungathered = b->peer_unsent;  // the launch pushes the step before (if it was still unsent)
