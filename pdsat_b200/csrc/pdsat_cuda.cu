@@ -638,6 +638,28 @@ int pdsat_batch_create(pdsat_db* db, int32_t n_points, const pdsat_point* points
         const uint64_t per_seg = (total_rounds + target - 1) / target;
         int m = 1;
         while ((1ull << m) < per_seg) m++;
+        // A batch alone on its device with a long stream (a neighbourhood of points): the bit
+        // generator dominates the jumps, and more warps per scheduler pay.  Cost model from the
+        // measurements in profiles/r02_plane_width.md: a warp alone on its scheduler needs 746
+        // cycles per round (303 instructions at IPC 0.41); w warps reach IPC 0.58 / 0.70 / 0.78 /
+        // 0.84 / 0.90 for w = 2 / 3 / 4 / 5-7 / >= 8 (the ALU pipe caps it at 0.91); a jump costs
+        // 0.43 us of the whole GPU.  Pick the power of two that minimises generator + jumps.
+        if (target == 592 && !getenv("PDSAT_MT_SEGMENTS")) {
+            double best = 0;
+            int best_m = m;
+            for (int mm = 1; mm <= m; mm++) {
+                uint64_t segs = 0;
+                for (auto& hp : b->pts)
+                    if (hp.mode == PDSAT_MODE_RANDOM_MT19937) segs += (hp.mt_rounds + (1ull << mm) - 1) >> mm;
+                const uint64_t w = (segs + 591) / 592;
+                const double ipc = w <= 1 ? 0.41 : w == 2 ? 0.58 : w == 3 ? 0.70 : w == 4 ? 0.78 : w < 8 ? 0.84 : 0.90;
+                const double gen_us = (double)(1ull << mm) * 303.0 * (double)w / ipc / 1900.0;
+                const double jump_us = 0.43 * (double)(segs - (uint64_t)b->n_mt_points);
+                const double t = gen_us + jump_us;
+                if (best == 0 || t < best) best = t, best_m = mm;
+            }
+            m = best_m;
+        }
         b->mt_m = m;
         uint32_t extra = 2u * (uint32_t)b->n_mt_points;  // slots 2p, 2p+1: ping-pong pair of point p
         uint64_t seg = 0;
